@@ -1,0 +1,180 @@
+/*
+ * tc_b200.h -- C ABI of libtc_b200.so: the B200 (sm_100a) implementation of the
+ * text-compression hot path (Data.BWT, Data.MTF, Data.RLE, Data.FMIndex).
+ *
+ * The reference (Matthew-Mosior/text-compression v0.1.0.25) is pure Haskell and has
+ * no FFI today; the boundary a maintainer binds with `foreign import ccall` is the
+ * "Internal" function set.  Each entry point below names the reference function it
+ * replaces (paths relative to the reference root).  See INTEGRATION.md for the
+ * Haskell-side stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns TC_OK (0) or a negative
+ *     TC_E_* code and never aborts.  TC_E_FROMJUST / TC_E_INDEX mark the inputs on
+ *     which the reference itself throws (`fromJust Nothing`, `DS.index` out of range).
+ *   - text symbols are uint8_t.  A `Seq (Maybe b)` is int16_t with -1 == Nothing
+ *     (the "$" sentinel, smaller than every Just) and 0..255 == Just byte.
+ *   - the `_u8` twins carry a BWT as uint8_t[N] plus `primary`, the 0-based slot
+ *     that holds the single Nothing (the byte stored in that slot is ignored).
+ *   - Haskell `Int` results are int64_t/uint64_t; ranks and positions are 1-based
+ *     wherever the reference's are.
+ *   - host entry points take HOST pointers (pageable or tc_host_alloc'ed) and do the
+ *     H2D/D2H copies themselves; `_dev` entry points take DEVICE pointers on the
+ *     context's device and enqueue on the context's stream.
+ *   - one tc_ctx per calling OS thread; distinct contexts are fully concurrent.
+ *   - sizes: n < 2^32 - 2 (TC_E_TOOBIG otherwise).
+ *   - there is NO CPU fallback: without a usable CUDA device tc_ctx_create fails
+ *     with TC_E_NODEVICE and nothing else can be called.
+ */
+#ifndef TC_B200_H
+#define TC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TC_OK 0
+#define TC_E_CUDA (-1)      /* CUDA runtime error; tc_last_error(ctx) has the text   */
+#define TC_E_CAP (-2)       /* output capacity too small; required size is returned  */
+#define TC_E_FROMJUST (-3)  /* the reference would throw `fromJust Nothing`           */
+#define TC_E_INDEX (-4)     /* the reference would throw `index out of bounds`       */
+#define TC_E_NOMEM (-5)
+#define TC_E_ARG (-6)
+#define TC_E_TOOBIG (-7)
+#define TC_E_NODEVICE (-8)
+
+typedef struct tc_ctx tc_ctx; /* device + stream + scratch arena */
+typedef struct tc_fm tc_fm;   /* device-resident FM-index */
+
+/* ---- context ------------------------------------------------------------- */
+int tc_ctx_create(int device, tc_ctx **out);
+/* Same, but enqueue on an existing cudaStream_t (e.g. torch's current stream). */
+int tc_ctx_create_on_stream(int device, void *cuda_stream, tc_ctx **out);
+void tc_ctx_destroy(tc_ctx *ctx);
+int tc_ctx_sync(tc_ctx *ctx);
+const char *tc_strerror(int rc);
+const char *tc_last_error(const tc_ctx *ctx);
+/* CUDA-pinned staging memory for the host entry points. */
+void *tc_host_alloc(size_t bytes);
+void tc_host_free(void *p);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t tc_ctx_launches(const tc_ctx *ctx);
+const char *tc_version(void);
+
+/* ---- Data.BWT -------------------------------------------------------------- */
+/* createSuffixArray + saToBWT + toBWT (src/Data/BWT/Internal.hs:98-134,
+ * src/Data/BWT.hs:55-64).  bwt[N=n+1]; *primary = slot of the Nothing;
+ * sa_1based (nullable) = suffixstartpos per rank.  n == 0: BWT Empty, *primary = 0. */
+int tc_bwt_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t *bwt, uint64_t *primary,
+                  uint32_t *sa_1based);
+/* fromBWT = sortTB + magicInverseBWT (src/Data/BWT.hs:93-104,
+ * src/Data/BWT/Internal.hs:144-200) on an arbitrary Seq (Maybe Word8). */
+int tc_bwt_decode(tc_ctx *ctx, const int16_t *bwt, uint64_t N, uint8_t *text, uint64_t cap, uint64_t *n_out);
+int tc_bwt_decode_u8(tc_ctx *ctx, const uint8_t *bwt, uint64_t N, uint64_t primary, uint8_t *text, uint64_t cap,
+                     uint64_t *n_out);
+
+/* ---- Data.MTF -------------------------------------------------------------- */
+/* seqToMTF (src/Data/MTF/Internal.hs:128-175): indices + the FINAL list. */
+int tc_mtf_encode(tc_ctx *ctx, const int16_t *sym, uint64_t N, uint16_t *idx, int16_t *final_list /*257*/,
+                  uint32_t *sigma);
+int tc_mtf_encode_u8(tc_ctx *ctx, const uint8_t *bwt, uint64_t N, uint64_t primary, uint16_t *idx,
+                     int16_t *final_list /*257*/, uint32_t *sigma);
+/* seqFromMTF (src/Data/MTF/Internal.hs:201-232): initial list = sort(final list). */
+int tc_mtf_decode(tc_ctx *ctx, const uint16_t *idx, uint64_t N, const int16_t *final_list, uint32_t sigma,
+                  int16_t *sym);
+
+/* ---- Data.RLE -------------------------------------------------------------- */
+/* seqToRLE (src/Data/RLE/Internal.hs:104-153) including its Nothing quirks.
+ * Run k is (count[k], rsym[k]); the reference's flat Seq is [show count, sym]...
+ * *R is always the true run count; R > cap gives TC_E_CAP with the first cap runs written. */
+int tc_rle_encode(tc_ctx *ctx, const int16_t *sym, uint64_t N, uint32_t *count, int16_t *rsym, uint64_t cap,
+                  uint64_t *R);
+int tc_rle_encode_u8(tc_ctx *ctx, const uint8_t *bwt, uint64_t N, uint64_t primary, uint32_t *count, int16_t *rsym,
+                     uint64_t cap, uint64_t *R);
+/* run-length over an MTF index stream (no Nothing can occur). */
+int tc_rle_encode_u16(tc_ctx *ctx, const uint16_t *idx, uint64_t N, uint32_t *count, int16_t *rsym, uint64_t cap,
+                      uint64_t *R);
+/* seqFromRLE (src/Data/RLE/Internal.hs:155-189): (Just _, Nothing) -> one Nothing,
+ * else count copies. *N is always the true length; N > cap gives TC_E_CAP. */
+int tc_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, int16_t *sym, uint64_t cap,
+                  uint64_t *N);
+
+/* ---- composed helpers (bytestringToBWTToRLEB-style, device-resident chaining) ---- */
+typedef struct {
+    uint64_t n;              /* text length                                    */
+    uint64_t N;              /* BWT length (n+1, or 0)                         */
+    uint64_t primary;        /* slot of the Nothing in the BWT                 */
+    uint32_t sigma;          /* MTF alphabet size incl. Nothing (0 if no MTF)  */
+    int16_t final_list[257]; /* MTF final list (seqToMTF's second component)   */
+    uint64_t R;              /* number of runs                                 */
+} tc_block_info;
+/* bytestringToBWTToRLEB (src/Data/RLE.hs:83-85): text -> BWT -> seqToRLE(symbols). */
+int tc_bwt_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *count, int16_t *rsym, uint64_t cap,
+                      tc_block_info *info);
+/* bytestringToBWTToMTFB (src/Data/MTF.hs:82-84) followed by seqToRLE over the index
+ * stream (the BWT+MTF+RLE composite of BASELINE.json). */
+int tc_bwt_mtf_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *count, int16_t *rsym, uint64_t cap,
+                          tc_block_info *info);
+/* inverses: runs -> (MTF indices ->) BWT -> text. */
+int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
+                      uint64_t cap, uint64_t *n_out);
+int tc_bwt_mtf_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, const tc_block_info *info,
+                          uint8_t *text, uint64_t cap, uint64_t *n_out);
+
+/* device-pointer twins used when the data is already in HBM (bench `value`). */
+int tc_bwt_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t *d_bwt, uint64_t *primary,
+                      uint32_t *d_sa_1based);
+int tc_mtf_encode_u8_dev(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
+                         int16_t *final_list, uint32_t *sigma);
+int tc_rle_encode_u8_dev(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint32_t *d_count,
+                         int16_t *d_rsym, uint64_t cap, uint64_t *R);
+int tc_rle_encode_u16_dev(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
+                          uint64_t cap, uint64_t *R);
+int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_count, int16_t *d_rsym,
+                              uint64_t cap, tc_block_info *info);
+
+/* ---- Data.FMIndex ------------------------------------------------------------ */
+/* *ToBWTToFMIndex* (src/Data/FMIndex.hs:108-183): C[c] (seqToCc, Internal.hs:275-316),
+ * Occ (seqToOccCK, :195-259; stored as rank-blocks instead of the dense table) and the
+ * suffix array (sampled every sa_sample_rate text positions; 1 keeps the full SA). */
+int tc_fm_build(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t sa_sample_rate, tc_fm **out);
+int tc_fm_build_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t sa_sample_rate, tc_fm **out);
+void tc_fm_free(tc_fm *fm);
+typedef struct {
+    uint64_t n, N, primary;
+    uint32_t sigma;       /* alphabet incl. Nothing */
+    uint32_t sa_sample_rate;
+    int16_t alphabet[257]; /* sorted, alphabet[0] == -1 */
+    int64_t C[257];        /* Cc: C[j] for alphabet[j] */
+    uint64_t blob_bytes;   /* size of the device image (tc_fm_blob) */
+    uint64_t n_samples;
+} tc_fm_info;
+int tc_fm_get_info(const tc_fm *fm, tc_fm_info *info);
+/* countFMIndex (src/Data/FMIndex/Internal.hs:347-438) for q patterns; pattern i is
+ * pats[off[i] .. off[i+1]).  count[i] == -1 is Nothing. */
+int tc_fm_count(tc_ctx *ctx, const tc_fm *fm, const uint8_t *pats, const uint64_t *off, uint64_t q, int64_t *count);
+int tc_fm_count_dev(tc_ctx *ctx, const tc_fm *fm, const uint8_t *d_pats, const uint64_t *d_off, uint64_t q,
+                    int64_t *d_count);
+/* locateFMIndex (:448-542) + the rank->position map of the wrappers
+ * (src/Data/FMIndex.hs:496,526,562,598): pattern i's hits are
+ * pos_1based[hit_off[i] .. hit_off[i+1]) in SA-rank order (the reference's order, unsorted).
+ * *total is always the true number of hits; total > cap gives TC_E_CAP. */
+int tc_fm_locate(tc_ctx *ctx, const tc_fm *fm, const uint8_t *pats, const uint64_t *off, uint64_t q,
+                 uint64_t *hit_off /*q+1*/, uint64_t *pos_1based, uint64_t cap, uint64_t *total);
+int tc_fm_locate_dev(tc_ctx *ctx, const tc_fm *fm, const uint8_t *d_pats, const uint64_t *d_off, uint64_t q,
+                     uint64_t *d_hit_off /*q+1*/, uint64_t *d_pos_1based, uint64_t cap, uint64_t *total);
+/* Materialise what the public FMIndex value holds (small N): BWT as maybe-symbols and,
+ * when built with sa_sample_rate == 1, the full 1-based suffix array. */
+int tc_fm_export(tc_ctx *ctx, const tc_fm *fm, int16_t *bwt /*N*/, uint32_t *sa_1based /*N, nullable*/);
+/* Replication across GPUs: the index is one contiguous device image.  Broadcast the
+ * image (NCCL) and re-open it on the peer with tc_fm_from_blob_dev. */
+const void *tc_fm_blob(const tc_fm *fm);
+int tc_fm_from_blob_dev(tc_ctx *ctx, void *d_blob, uint64_t bytes, int take_ownership, tc_fm **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TC_B200_H */

@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs, bit-exact.  Run on the B200 box with `-m gpu`."""
+import numpy as np
+import pytest
+
+from tests.util import gen_acgt, gen_acgtn, gen_ascii, gen_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from text_compression_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _maybe_stream(rng, n, alpha, p_nothing):
+    x = rng.choice(np.asarray(alpha, dtype=np.int16), size=n).astype(np.int16)
+    if p_nothing > 0 and n:
+        x[rng.random(n) < p_nothing] = -1
+    return x
+
+
+SIZES = [0, 1, 2, 3, 5, 17, 255, 256, 257, 2047, 2048, 2049, 4095, 4096, 4097, 8193, 70001, 300007]
+
+
+# ---------------------------------------------------------------- RLE
+@pytest.mark.parametrize("n", SIZES)
+def test_rle_encode_i16(ctx, orc, n):
+    from text_compression_b200.rle import seqToRLE, seqFromRLE
+    from text_compression_b200.seq import MaybeSeq
+    rng = np.random.default_rng(n + 1)
+    for alpha, pn in (([65, 67], 0.0), ([65, 67, 71, 84], 0.02), ([65], 0.3), (list(range(256)), 0.01), ([7], 1.0)):
+        x = _maybe_stream(rng, n, alpha, pn)
+        got = seqToRLE(MaybeSeq(x, "B"), ctx)
+        cnt, sym = orc.rle_encode(x)
+        assert got.counts.tolist() == cnt.tolist() and got.syms.tolist() == sym.tolist(), (n, alpha[:4], pn)
+        dec = seqFromRLE(got, ctx)
+        assert dec.codes.tolist() == orc.rle_decode(cnt, sym).tolist()
+
+
+def test_rle_quirks(ctx, orc):
+    from text_compression_b200.rle import seqToRLE
+    from text_compression_b200.seq import MaybeSeq
+    cases = [[-1], [-1, -1], [97], [97, -1], [-1, 97, 97, 98], [97, 97, -1, -1, 98], [97, -1, 98, -1],
+             [97, 97, 97, 97], [-1, -1, -1, 97, -1, -1]]
+    for c in cases:
+        x = np.array(c, dtype=np.int16)
+        got = seqToRLE(MaybeSeq(x, "B"), ctx)
+        cnt, sym = orc.rle_encode(x)
+        assert list(zip(got.counts.tolist(), got.syms.tolist())) == list(zip(cnt.tolist(), sym.tolist())), c
+
+
+@pytest.mark.parametrize("n", [1, 16, 4096, 4097, 100003])
+def test_rle_u8_u16(ctx, orc, n):
+    import ctypes as C
+    from text_compression_b200._lib import ptr
+    rng = np.random.default_rng(n)
+    for alpha in ([65, 67, 71, 84], list(range(256))):
+        b = rng.choice(np.asarray(alpha, dtype=np.uint8), size=n).astype(np.uint8)
+        for primary in sorted({0, n // 2, n - 1, n + 5}):
+            x = b.astype(np.int16)
+            if primary < n:
+                x[primary] = -1
+            cnt, sym = orc.rle_encode(x)
+            cap = n + 3
+            oc, os_ = np.empty(cap, np.uint32), np.empty(cap, np.int16)
+            R = C.c_uint64(0)
+            ctx.call("tc_rle_encode_u8", ptr(b), n, primary, ptr(oc), ptr(os_), cap, C.byref(R))
+            assert oc[:R.value].tolist() == cnt.tolist() and os_[:R.value].tolist() == sym.tolist(), (n, primary)
+        idx = rng.integers(0, 257, size=n).astype(np.uint16)
+        idx[rng.random(n) < 0.5] = 0
+        cnt, sym = orc.rle_encode(idx.astype(np.int16))
+        oc, os_ = np.empty(n + 1, np.uint32), np.empty(n + 1, np.int16)
+        R = C.c_uint64(0)
+        ctx.call("tc_rle_encode_u16", ptr(idx), n, ptr(oc), ptr(os_), n + 1, C.byref(R))
+        assert oc[:R.value].tolist() == cnt.tolist() and os_[:R.value].tolist() == sym.tolist()
+
+
+def test_rle_cap(ctx):
+    import ctypes as C
+    from text_compression_b200._lib import ptr, TC_E_CAP
+    x = np.arange(100, dtype=np.int16) % 7
+    oc, os_ = np.empty(10, np.uint32), np.empty(10, np.int16)
+    R = C.c_uint64(0)
+    rc = ctx.call("tc_rle_encode", ptr(x), 100, ptr(oc), ptr(os_), 10, C.byref(R), allow=(TC_E_CAP,))
+    assert rc == TC_E_CAP and R.value == 100
+
+
+def test_rle_decode_long_runs(ctx, orc):
+    from text_compression_b200.rle import seqFromRLE
+    from text_compression_b200.seq import RLE
+    cnt = np.array([100000, 1, 0, 3, 50000, 7, 1], dtype=np.uint32)
+    sym = np.array([65, -1, 66, 67, 68, -1, 69], dtype=np.int16)
+    got = seqFromRLE(RLE(cnt, sym, "B"), ctx)
+    assert got.codes.tolist() == orc.rle_decode(cnt.astype(np.int64), sym).tolist()
+
+
+# ---------------------------------------------------------------- MTF
+@pytest.mark.parametrize("n", SIZES)
+def test_mtf_roundtrip_and_parity(ctx, orc, n):
+    from text_compression_b200.mtf import seqToMTF, seqFromMTF
+    from text_compression_b200.seq import MaybeSeq
+    rng = np.random.default_rng(n + 7)
+    for alpha, pn in (([65, 67, 71, 84], 0.001), (list(range(256)), 0.001), ([120], 0.0), (list(range(32, 127)), 0.0),
+                      ([3, 200], 0.4)):
+        x = _maybe_stream(rng, n, alpha, pn)
+        got = seqToMTF(MaybeSeq(x, "B"), ctx)
+        idx, fin = orc.mtf_encode(x)
+        assert got.final_list.codes.tolist() == fin.tolist(), (n, len(alpha))
+        bad = np.nonzero(got.indices != idx)[0]
+        assert bad.size == 0, (n, len(alpha), bad[:5], got.indices[bad[:5]], idx[bad[:5]])
+        dec = seqFromMTF(got, ctx)
+        assert dec.codes.tolist() == x.tolist(), (n, len(alpha))
+
+
+def test_mtf_skewed_large(ctx, orc):
+    from text_compression_b200.mtf import seqToMTF, seqFromMTF
+    from text_compression_b200.seq import MaybeSeq
+    rng = np.random.default_rng(5)
+    n = 1_000_003
+    x = rng.choice(np.arange(256, dtype=np.int16), size=n, p=np.r_[[0.9], np.full(255, 0.1 / 255)]).astype(np.int16)
+    x[123456] = -1
+    got = seqToMTF(MaybeSeq(x, "B"), ctx)
+    idx, fin = orc.mtf_encode(x)
+    assert got.final_list.codes.tolist() == fin.tolist()
+    assert np.array_equal(got.indices, idx)
+    assert np.array_equal(seqFromMTF(got, ctx).codes, x)
+
+
+def test_mtf_decode_bad_index(ctx):
+    from text_compression_b200 import SeqIndexError
+    from text_compression_b200.mtf import seqFromMTF
+    from text_compression_b200.seq import MTF, MaybeSeq
+    m = MTF(np.array([0, 1, 5], dtype=np.int64), MaybeSeq(np.array([97, 98, -1], dtype=np.int16), "B"))
+    with pytest.raises(SeqIndexError):
+        seqFromMTF(m, ctx)
+
+
+# ---------------------------------------------------------------- BWT
+def _bwt_cases():
+    rng = np.random.default_rng(11)
+    yield "empty", np.empty(0, np.uint8)
+    for n in (1, 2, 3, 4, 31, 1000, 4097, 65536):
+        yield f"acgt{n}", gen_acgt(0xC1, n)
+        yield f"bytes{n}", gen_bytes(0xC2, n)
+    yield "a", np.frombuffer(b"a", np.uint8)
+    yield "ba", np.frombuffer(b"ba", np.uint8)
+    yield "aaaa", np.full(5000, 97, np.uint8)
+    yield "abab", np.tile(np.frombuffer(b"ab", np.uint8), 3000)
+    yield "period7", np.tile(gen_acgt(3, 7), 2000)
+    yield "fib", _fib(16)
+    yield "twobytes", rng.integers(0, 2, 20000).astype(np.uint8) * 255
+    yield "zeros_in_text", rng.integers(0, 3, 5000).astype(np.uint8)
+    yield "ascii", gen_ascii(0xC2B, 50000)
+    yield "acgtn", gen_acgtn(0xC3, 200000)
+
+
+def _fib(k):
+    a, b = b"a", b"ab"
+    for _ in range(k):
+        a, b = b, b + a
+    return np.frombuffer(b, np.uint8)
+
+
+@pytest.mark.parametrize("name,text", list(_bwt_cases()), ids=[c[0] for c in _bwt_cases()])
+def test_bwt_encode_decode(ctx, orc, name, text):
+    from text_compression_b200.bwt import bwt_u8, toBWT, fromBWT, createSuffixArray
+    bwt, primary, sa = bwt_u8(text, want_sa=True, ctx=ctx)
+    want_bwt, want_sa = orc.bwt_encode(text, want_sa=True)
+    got = toBWT(text, ctx).seq.codes
+    assert got.size == want_bwt.size
+    if text.size:
+        assert sa.tolist() == want_sa.tolist(), name
+        assert got.tolist() == want_bwt.tolist(), name
+        assert primary == int(np.nonzero(want_bwt < 0)[0][0])
+    from text_compression_b200.seq import BWT, MaybeSeq
+    back = fromBWT(BWT(MaybeSeq(got, "W")), ctx)
+    assert bytes(back) == text.tobytes(), name
+
+
+def test_bwt_decode_malformed(ctx, orc):
+    from text_compression_b200 import FromJustError
+    from text_compression_b200.bwt import fromBWT
+    from text_compression_b200.seq import BWT, MaybeSeq
+    rng = np.random.default_rng(3)
+    # no Nothing -> empty (src/Data/BWT/Internal.hs:174-175)
+    assert fromBWT(BWT(MaybeSeq(np.array([97, 98, 99], np.int16), "W")), ctx) == []
+    n_err = n_ok = 0
+    for trial in range(60):
+        n = int(rng.integers(1, 400))
+        x = rng.integers(97, 100, size=n).astype(np.int16)
+        k = 1 if trial % 2 == 0 else int(rng.integers(1, 4))
+        x[rng.choice(n, size=min(k, n), replace=False)] = -1
+        try:
+            want = orc.bwt_decode(x).tolist()
+            werr = False
+        except orc.OracleError as e:
+            assert e.rc == orc.ORC_E_FROMJUST
+            werr = True
+        if werr:
+            with pytest.raises(FromJustError):
+                fromBWT(BWT(MaybeSeq(x, "W")), ctx)
+            n_err += 1
+        else:
+            assert fromBWT(BWT(MaybeSeq(x, "W")), ctx) == want, x.tolist()
+            n_ok += 1
+    assert n_ok > 0
+
+
+# ---------------------------------------------------------------- reference's own tests, through the API
+def test_reference_hunit_vectors(ctx, golden):
+    from text_compression_b200 import rle as R, mtf as M
+    from text_compression_b200.seq import MTF, RLE, MaybeSeq
+    r1, r2 = golden["rle"]
+    # Data/RLE.hs:316-319
+    assert R.textToBWTToRLET(r1["text"], ctx).to_list() == r1["rle"]
+    assert R.textToBWTToRLEB(r2["text"], ctx).to_list() == [None if x is None else x.encode() for x in r2["rle"]]
+    assert R.textFromBWTFromRLET(RLE.from_list(r1["rle"], "T"), ctx) == r1["text"]
+    assert R.textFromBWTFromRLET(RLE.from_list(r2["rle"], "T"), ctx) == r2["text"]
+    # Data/MTF.hs:290-298
+    m = golden["mtf"][0]
+    got = M.textToBWTToMTFB(m["text"], ctx)
+    assert got.to_tuple() == (m["indices"], [None if x is None else x.encode() for x in m["final_list"]])
+    mm = MTF(np.array(m["indices"], np.int64), MaybeSeq.from_list([None if x is None else x.encode() for x in m["final_list"]], "B"))
+    assert M.textFromBWTFromMTFB(mm, ctx) == m["text"]
+
+
+def test_fm_doc_tables(ctx, golden):
+    from text_compression_b200 import fmindex as F
+    d = golden["fmindex_doc"]
+    fm = F.textToBWTToFMIndexT(d["text"], ctx=ctx)
+    assert "".join("$" if c is None else c for c in F.textFromFMIndexT(fm).to_list()) == d["bwt"]
+    assert fm.Cc == list(zip(d["C_vals"], [None if c == "$" else c for c in d["C_syms"]]))
+    occ = fm.OccCK
+    for (sym, row), c in zip(occ, d["C_syms"]):
+        assert [o for (_, o, _) in row] == d["occ"][c]
+    assert F.countFMIndex("abra", fm) == 2
+    assert F.locateFMIndex("abra", fm) == [8, 1]
+    assert F.locateFMIndex("a", fm) == [11, 8, 1, 4, 6]
+    assert F.countFMIndex("xa", fm) == 5 and F.countFMIndex("ax", fm) is None and F.countFMIndex("", fm) is None
+    assert F.textFMIndexCountS(["abra", "zzz", "a"], d["text"], ctx=ctx) == [("abra", 2), ("zzz", None), ("a", 5)]
+    assert F.bytestringFMIndexLocateS([b"abra"], d["text"].encode(), ctx=ctx) == [(b"abra", [8, 1])]
+    assert F.bytestringFMIndexCountS([], b"abc", ctx=ctx) == [] and F.bytestringFMIndexCountS([b"a"], b"", ctx=ctx) == []
+
+
+# ---------------------------------------------------------------- FM-index vs oracle
+@pytest.mark.parametrize("rate", [1, 4, 32])
+def test_fm_count_locate(ctx, orc, rate):
+    from text_compression_b200.fmindex import FMIndex
+    rng = np.random.default_rng(rate)
+    text = gen_acgtn(0xC3, 60000)
+    fm = FMIndex(text, "B", rate, ctx)
+    ofm = orc.FMIndex(text)
+    assert fm.Cc[0][0] == 0 and [c for c, _ in fm.Cc] == ofm.Cc.tolist()
+    pats = []
+    for _ in range(3000):
+        m = int(rng.integers(1, 40))
+        o = int(rng.integers(0, text.size - m))
+        p = text[o:o + m].copy()
+        u = rng.random()
+        if u < 0.15:
+            p[rng.integers(0, m)] = rng.choice(np.frombuffer(b"ACGTNXZ", np.uint8))
+        pats.append(p.tobytes())
+    pats += [b"", b"X", b"AX", b"XA", b"A", b"N", b"NN"]
+    got = fm.count_many(pats)
+    want = np.array([ofm.count(p) for p in pats])
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+    sel = [p for p in pats if len(p) >= 3][:600] + [b"AC", b"XA", b""]
+    ho, pos = fm.locate_many(sel)
+    for i, p in enumerate(sel):
+        assert pos[ho[i]:ho[i + 1]].tolist() == ofm.locate(p).tolist(), (i, p)
+    if rate == 1:
+        assert [s for _, s in fm.SA] == ofm.sa.tolist()
+    fm.close()
+
+
+def test_fm_bytes_alphabet(ctx, orc):
+    from text_compression_b200.fmindex import FMIndex
+    text = gen_bytes(9, 30000)
+    fm = FMIndex(text, "B", 16, ctx)
+    ofm = orc.FMIndex(text[:30000])
+    pats = [text[o:o + 3].tobytes() for o in range(0, 3000, 7)] + [bytes([1, 2, 3, 4, 5])]
+    assert fm.count_many(pats).tolist() == [ofm.count(p) for p in pats]
+    ho, pos = fm.locate_many(pats[:50])
+    for i, p in enumerate(pats[:50]):
+        assert pos[ho[i]:ho[i + 1]].tolist() == ofm.locate(p).tolist()
+
+
+# ---------------------------------------------------------------- composed helpers
+@pytest.mark.parametrize("gen,n", [(gen_acgt, 65536), (gen_bytes, 100000), (gen_acgtn, 30011), (gen_ascii, 4096)])
+def test_composites(ctx, orc, gen, n):
+    from text_compression_b200 import block
+    text = gen(0xC1, n)
+    bwt = orc.bwt_encode(text)
+    b1 = block.compress_bwt_rle(text, ctx)
+    cnt, sym = orc.rle_encode(bwt)
+    assert b1.counts.tolist() == cnt.tolist() and b1.syms.tolist() == sym.tolist()
+    assert block.decompress(b1, ctx) == text.tobytes()
+    b2 = block.compress_bwt_mtf_rle(text, ctx)
+    idx, fin = orc.mtf_encode(bwt)
+    cnt, sym = orc.rle_encode(idx.astype(np.int16))
+    assert b2.final_list.tolist() == fin.tolist()
+    assert b2.counts.tolist() == cnt.tolist() and b2.syms.tolist() == sym.tolist()
+    assert block.decompress(b2, ctx) == text.tobytes()
+
+
+def test_q1_trailing_nothing_stream(ctx, orc):
+    """Texts that are their own greatest suffix: the reference's RLE re-emits a stale pair (Q1)
+    and its own round trip breaks; the GPU stream must equal the oracle's, not round-trip."""
+    from text_compression_b200 import block
+    for t in (b"a", b"ba", b"aaaa", b"cba"):
+        b1 = block.compress_bwt_rle(t, ctx)
+        cnt, sym = orc.rle_encode(orc.bwt_encode(t))
+        assert list(zip(b1.counts.tolist(), b1.syms.tolist())) == list(zip(cnt.tolist(), sym.tolist())), t
+
+
+# ---------------------------------------------------------------- full-size properties
+def test_block_16mib_roundtrip(ctx):
+    from text_compression_b200 import block
+    text = gen_bytes(0xC2, 16 << 20)
+    blk = block.compress_bwt_mtf_rle(text, ctx)
+    assert blk.N == text.size + 1 and int(blk.counts.sum()) == blk.N      # run lengths cover the BWT
+    assert sorted(blk.final_list.tolist()) == [-1] + list(range(256))
+    assert block.decompress(blk, ctx) == text.tobytes()

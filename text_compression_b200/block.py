@@ -1,0 +1,76 @@
+"""Composed helpers with device-resident chaining.
+
+  compress_bwt_rle      = bytestringToBWTToRLEB            (src/Data/RLE.hs:83-85)
+  compress_bwt_mtf_rle  = bytestringToBWTToMTFB, then seqToRLE over the index stream
+                          (the "BWT+MTF+RLE" composite of BASELINE.json)
+BWT -> MTF -> RLE never leaves HBM; only the text goes in and the runs come out.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import TC_E_CAP, BlockInfo, default_context, ptr
+from .seq import to_bytes
+
+
+@dataclass
+class CompressedBlock:
+    n: int
+    N: int
+    primary: int
+    sigma: int
+    final_list: np.ndarray   # int16[sigma]; empty when MTF was not applied
+    counts: np.ndarray       # uint32[R]
+    syms: np.ndarray         # int16[R]: BWT symbols (-1 == Nothing) or MTF indices
+    with_mtf: bool
+
+    @property
+    def R(self) -> int:
+        return int(self.counts.size)
+
+
+def _compress(fn, text, ctx, with_mtf) -> CompressedBlock:
+    ctx = ctx or default_context()
+    t = text if isinstance(text, np.ndarray) else np.frombuffer(to_bytes(text), dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    n = t.size
+    cap = n + 3
+    cnt = np.empty(cap, dtype=np.uint32)
+    sym = np.empty(cap, dtype=np.int16)
+    info = BlockInfo()
+    ctx.call(fn, ptr(t), n, ptr(cnt), ptr(sym), cap, C.byref(info))
+    R = int(info.R)
+    fin = np.array(info.final_list[: info.sigma], dtype=np.int16)
+    return CompressedBlock(n, int(info.N), int(info.primary), int(info.sigma), fin, cnt[:R].copy(), sym[:R].copy(),
+                           with_mtf)
+
+
+def compress_bwt_rle(text, ctx=None) -> CompressedBlock:
+    return _compress("tc_bwt_rle_encode", text, ctx, False)
+
+
+def compress_bwt_mtf_rle(text, ctx=None) -> CompressedBlock:
+    return _compress("tc_bwt_mtf_rle_encode", text, ctx, True)
+
+
+def decompress(blk: CompressedBlock, ctx=None) -> bytes:
+    ctx = ctx or default_context()
+    if blk.R == 0:
+        return b""
+    cap = max(blk.n, 1) + 2
+    out = np.empty(cap, dtype=np.uint8)
+    n_out = C.c_uint64(0)
+    cnt = np.ascontiguousarray(blk.counts, dtype=np.uint32)
+    sym = np.ascontiguousarray(blk.syms, dtype=np.int16)
+    if blk.with_mtf:
+        info = BlockInfo()
+        info.n, info.N, info.primary, info.sigma, info.R = blk.n, blk.N, blk.primary, blk.sigma, blk.R
+        for j, v in enumerate(blk.final_list.tolist()):
+            info.final_list[j] = v
+        ctx.call("tc_bwt_mtf_rle_decode", ptr(cnt), ptr(sym), C.byref(info), ptr(out), cap, C.byref(n_out))
+    else:
+        ctx.call("tc_bwt_rle_decode", ptr(cnt), ptr(sym), blk.R, ptr(out), cap, C.byref(n_out))
+    return out[: n_out.value].tobytes()

@@ -1,0 +1,374 @@
+// api.cu -- the extern "C" entry points of include/tc_b200.h for BWT / MTF / RLE and the
+// composed helpers.  Host entry points stage through the scratch arena (H2D, kernels, D2H on
+// the context's stream); `_dev` entry points work on device pointers.  Every entry point
+// resets the arena exactly once; the *_impl functions never do.
+#include "common.cuh"
+#include "impl.cuh"
+
+#define TC_ENTER(ctx)                  \
+    do {                               \
+        if (!(ctx)) return TC_E_ARG;   \
+        TC_TRY(tc_ws_reset(ctx));      \
+    } while (0)
+
+namespace {
+template <typename T>
+int h2d(tc_ctx *ctx, T *dst, const T *src, size_t count) {
+    if (count) TC_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return TC_OK;
+}
+template <typename T>
+int d2h(tc_ctx *ctx, T *dst, const T *src, size_t count) {
+    if (count) TC_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    return TC_OK;
+}
+int sync(tc_ctx *ctx) {
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TC_OK;
+}
+} // namespace
+
+// ---- Data.BWT ------------------------------------------------------------------
+extern "C" int tc_bwt_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t *d_bwt, uint64_t *primary,
+                                 uint32_t *d_sa_1based) {
+    TC_ENTER(ctx);
+    if (!primary) return TC_E_ARG;
+    return bwt_encode_dev_impl(ctx, d_text, n, d_bwt, primary, d_sa_1based);
+}
+
+extern "C" int tc_bwt_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint8_t *bwt, uint64_t *primary,
+                             uint32_t *sa_1based) {
+    TC_ENTER(ctx);
+    if (!primary) return TC_E_ARG;
+    *primary = 0;
+    if (n == 0) return TC_OK;
+    if (n + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+    uint8_t *d_text, *d_bwt;
+    uint32_t *d_sa1 = nullptr;
+    TC_TRY(ws_alloc(ctx, n, &d_text));
+    TC_TRY(ws_alloc(ctx, n + 1, &d_bwt));
+    if (sa_1based) TC_TRY(ws_alloc(ctx, n + 1, &d_sa1));
+    TC_TRY(h2d(ctx, d_text, text, n));
+    TC_TRY(bwt_encode_dev_impl(ctx, d_text, n, d_bwt, primary, d_sa1));
+    TC_TRY(d2h(ctx, bwt, d_bwt, n + 1));
+    if (sa_1based) TC_TRY(d2h(ctx, sa_1based, d_sa1, n + 1));
+    return sync(ctx);
+}
+
+extern "C" int tc_bwt_decode(tc_ctx *ctx, const int16_t *bwt, uint64_t N, uint8_t *text, uint64_t cap,
+                             uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out) return TC_E_ARG;
+    *n_out = 0;
+    if (N == 0) return TC_OK;
+    int16_t *d_bwt;
+    uint8_t *d_text;
+    TC_TRY(ws_alloc(ctx, N, &d_bwt));
+    TC_TRY(ws_alloc(ctx, N, &d_text));
+    TC_TRY(h2d(ctx, d_bwt, bwt, N));
+    int rc = bwt_decode_i16_dev_impl(ctx, d_bwt, N, d_text, N, n_out);
+    if (rc != TC_OK) return rc;
+    uint64_t m = *n_out < cap ? *n_out : cap;
+    TC_TRY(d2h(ctx, text, d_text, m));
+    TC_TRY(sync(ctx));
+    return *n_out > cap ? TC_E_CAP : TC_OK;
+}
+
+extern "C" int tc_bwt_decode_u8(tc_ctx *ctx, const uint8_t *bwt, uint64_t N, uint64_t primary, uint8_t *text,
+                                uint64_t cap, uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out) return TC_E_ARG;
+    *n_out = 0;
+    if (N == 0) return TC_OK;
+    uint8_t *d_bwt, *d_text;
+    TC_TRY(ws_alloc(ctx, N, &d_bwt));
+    TC_TRY(ws_alloc(ctx, N, &d_text));
+    TC_TRY(h2d(ctx, d_bwt, bwt, N));
+    int rc = bwt_decode_u8_dev_impl(ctx, d_bwt, N, primary, d_text, N, n_out);
+    if (rc != TC_OK) return rc;
+    uint64_t m = *n_out < cap ? *n_out : cap;
+    TC_TRY(d2h(ctx, text, d_text, m));
+    TC_TRY(sync(ctx));
+    return *n_out > cap ? TC_E_CAP : TC_OK;
+}
+
+// ---- Data.MTF ------------------------------------------------------------------
+extern "C" int tc_mtf_encode_u8_dev(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
+                                    int16_t *final_list, uint32_t *sigma) {
+    TC_ENTER(ctx);
+    if (!sigma || !final_list) return TC_E_ARG;
+    return mtf_encode_u8_dev_impl(ctx, d_bwt, N, primary, d_idx, final_list, sigma);
+}
+
+extern "C" int tc_mtf_encode(tc_ctx *ctx, const int16_t *sym, uint64_t N, uint16_t *idx, int16_t *final_list,
+                             uint32_t *sigma) {
+    TC_ENTER(ctx);
+    if (!sigma || !final_list) return TC_E_ARG;
+    *sigma = 0;
+    if (N == 0) return TC_OK;
+    int16_t *d_sym;
+    uint16_t *d_idx;
+    TC_TRY(ws_alloc(ctx, N, &d_sym));
+    TC_TRY(ws_alloc(ctx, N, &d_idx));
+    TC_TRY(h2d(ctx, d_sym, sym, N));
+    TC_TRY(mtf_encode_i16_dev_impl(ctx, d_sym, N, d_idx, final_list, sigma));
+    TC_TRY(d2h(ctx, idx, d_idx, N));
+    return sync(ctx);
+}
+
+extern "C" int tc_mtf_encode_u8(tc_ctx *ctx, const uint8_t *bwt, uint64_t N, uint64_t primary, uint16_t *idx,
+                                int16_t *final_list, uint32_t *sigma) {
+    TC_ENTER(ctx);
+    if (!sigma || !final_list) return TC_E_ARG;
+    *sigma = 0;
+    if (N == 0) return TC_OK;
+    uint8_t *d_bwt;
+    uint16_t *d_idx;
+    TC_TRY(ws_alloc(ctx, N, &d_bwt));
+    TC_TRY(ws_alloc(ctx, N, &d_idx));
+    TC_TRY(h2d(ctx, d_bwt, bwt, N));
+    TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, primary, d_idx, final_list, sigma));
+    TC_TRY(d2h(ctx, idx, d_idx, N));
+    return sync(ctx);
+}
+
+extern "C" int tc_mtf_decode(tc_ctx *ctx, const uint16_t *idx, uint64_t N, const int16_t *final_list, uint32_t sigma,
+                             int16_t *sym) {
+    TC_ENTER(ctx);
+    if (N == 0 || sigma == 0) return TC_OK;
+    if (!final_list) return TC_E_ARG;
+    uint16_t *d_idx;
+    int16_t *d_sym;
+    TC_TRY(ws_alloc(ctx, N, &d_idx));
+    TC_TRY(ws_alloc(ctx, N, &d_sym));
+    TC_TRY(h2d(ctx, d_idx, idx, N));
+    TC_TRY(mtf_decode_dev_impl(ctx, d_idx, N, final_list, sigma, d_sym));
+    TC_TRY(d2h(ctx, sym, d_sym, N));
+    return sync(ctx);
+}
+
+// ---- Data.RLE ------------------------------------------------------------------
+extern "C" int tc_rle_encode_u8_dev(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary,
+                                    uint32_t *d_count, int16_t *d_rsym, uint64_t cap, uint64_t *R) {
+    TC_ENTER(ctx);
+    if (!R) return TC_E_ARG;
+    return rle_encode_u8_dev_impl(ctx, d_bwt, N, primary, d_count, d_rsym, cap, R);
+}
+extern "C" int tc_rle_encode_u16_dev(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count,
+                                     int16_t *d_rsym, uint64_t cap, uint64_t *R) {
+    TC_ENTER(ctx);
+    if (!R) return TC_E_ARG;
+    return rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, R);
+}
+
+namespace {
+// shared tail of the host RLE encoders: runs are produced into arena buffers sized for the
+// worst case, then the first min(R, cap) are copied out.
+template <class F>
+int rle_encode_host(tc_ctx *ctx, uint64_t N, uint64_t worst, uint32_t *count, int16_t *rsym, uint64_t cap, uint64_t *R,
+                    F run) {
+    *R = 0;
+    if (N == 0) return TC_OK;
+    uint32_t *d_count;
+    int16_t *d_rsym;
+    TC_TRY(ws_alloc(ctx, worst, &d_count));
+    TC_TRY(ws_alloc(ctx, worst, &d_rsym));
+    int rc = run(d_count, d_rsym, worst);
+    if (rc != TC_OK) return rc;
+    uint64_t m = *R < cap ? *R : cap;
+    TC_TRY(d2h(ctx, count, d_count, m));
+    TC_TRY(d2h(ctx, rsym, d_rsym, m));
+    TC_TRY(sync(ctx));
+    return *R > cap ? TC_E_CAP : TC_OK;
+}
+} // namespace
+
+extern "C" int tc_rle_encode(tc_ctx *ctx, const int16_t *sym, uint64_t N, uint32_t *count, int16_t *rsym,
+                             uint64_t cap, uint64_t *R) {
+    TC_ENTER(ctx);
+    if (!R) return TC_E_ARG;
+    int16_t *d_sym = nullptr;
+    if (N) {
+        TC_TRY(ws_alloc(ctx, N, &d_sym));
+        TC_TRY(h2d(ctx, d_sym, sym, N));
+    }
+    return rle_encode_host(ctx, N, 2 * N + 1, count, rsym, cap, R, [&](uint32_t *dc, int16_t *ds, uint64_t w) {
+        return rle_encode_i16_dev_impl(ctx, d_sym, N, dc, ds, w, R);
+    });
+}
+
+extern "C" int tc_rle_encode_u8(tc_ctx *ctx, const uint8_t *bwt, uint64_t N, uint64_t primary, uint32_t *count,
+                                int16_t *rsym, uint64_t cap, uint64_t *R) {
+    TC_ENTER(ctx);
+    if (!R) return TC_E_ARG;
+    uint8_t *d_bwt = nullptr;
+    if (N) {
+        TC_TRY(ws_alloc(ctx, N, &d_bwt));
+        TC_TRY(h2d(ctx, d_bwt, bwt, N));
+    }
+    return rle_encode_host(ctx, N, N + 2, count, rsym, cap, R, [&](uint32_t *dc, int16_t *ds, uint64_t w) {
+        return rle_encode_u8_dev_impl(ctx, d_bwt, N, primary, dc, ds, w, R);
+    });
+}
+
+extern "C" int tc_rle_encode_u16(tc_ctx *ctx, const uint16_t *idx, uint64_t N, uint32_t *count, int16_t *rsym,
+                                 uint64_t cap, uint64_t *R) {
+    TC_ENTER(ctx);
+    if (!R) return TC_E_ARG;
+    uint16_t *d_idx = nullptr;
+    if (N) {
+        TC_TRY(ws_alloc(ctx, N, &d_idx));
+        TC_TRY(h2d(ctx, d_idx, idx, N));
+    }
+    return rle_encode_host(ctx, N, N + 1, count, rsym, cap, R, [&](uint32_t *dc, int16_t *ds, uint64_t w) {
+        return rle_encode_u16_dev_impl(ctx, d_idx, N, dc, ds, w, R);
+    });
+}
+
+extern "C" int tc_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, int16_t *sym,
+                             uint64_t cap, uint64_t *N) {
+    TC_ENTER(ctx);
+    if (!N) return TC_E_ARG;
+    *N = 0;
+    if (R == 0) return TC_OK;
+    uint32_t *d_count;
+    int16_t *d_rsym, *d_sym;
+    TC_TRY(ws_alloc(ctx, R, &d_count));
+    TC_TRY(ws_alloc(ctx, R, &d_rsym));
+    TC_TRY(ws_alloc(ctx, cap ? cap : 1, &d_sym));
+    TC_TRY(h2d(ctx, d_count, count, R));
+    TC_TRY(h2d(ctx, d_rsym, rsym, R));
+    int rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_sym, cap, N);
+    if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    uint64_t m = *N < cap ? *N : cap;
+    TC_TRY(d2h(ctx, sym, d_sym, m));
+    TC_TRY(sync(ctx));
+    return rc;
+}
+
+// ---- composed helpers --------------------------------------------------------------------
+namespace {
+void info_clear(tc_block_info *info, uint64_t n) {
+    memset(info, 0, sizeof *info);
+    info->n = n;
+}
+
+// text (device) -> BWT -> [MTF ->] RLE, everything stays in HBM.
+int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, uint32_t *d_count, int16_t *d_rsym,
+                 uint64_t cap, tc_block_info *info) {
+    info_clear(info, n);
+    if (n == 0) return TC_OK;
+    const uint64_t N = n + 1;
+    uint8_t *d_bwt;
+    TC_TRY(ws_alloc(ctx, N, &d_bwt));
+    TC_TRY(bwt_encode_dev_impl(ctx, d_text, n, d_bwt, &info->primary, nullptr));
+    info->N = N;
+    if (!with_mtf) return rle_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_count, d_rsym, cap, &info->R);
+    uint16_t *d_idx;
+    TC_TRY(ws_alloc(ctx, N, &d_idx));
+    TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma));
+    return rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R);
+}
+
+int compress_host(tc_ctx *ctx, const uint8_t *text, uint64_t n, bool with_mtf, uint32_t *count, int16_t *rsym,
+                  uint64_t cap, tc_block_info *info) {
+    if (!info) return TC_E_ARG;
+    info_clear(info, n);
+    if (n == 0) return TC_OK;
+    if (n + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+    uint8_t *d_text;
+    uint32_t *d_count;
+    int16_t *d_rsym;
+    const uint64_t worst = n + 3;
+    TC_TRY(ws_alloc(ctx, n, &d_text));
+    TC_TRY(ws_alloc(ctx, worst, &d_count));
+    TC_TRY(ws_alloc(ctx, worst, &d_rsym));
+    TC_TRY(h2d(ctx, d_text, text, n));
+    int rc = compress_dev(ctx, d_text, n, with_mtf, d_count, d_rsym, worst, info);
+    if (rc != TC_OK) return rc;
+    uint64_t m = info->R < cap ? info->R : cap;
+    TC_TRY(d2h(ctx, count, d_count, m));
+    TC_TRY(d2h(ctx, rsym, d_rsym, m));
+    TC_TRY(sync(ctx));
+    return info->R > cap ? TC_E_CAP : TC_OK;
+}
+} // namespace
+
+extern "C" int tc_bwt_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *count, int16_t *rsym,
+                                 uint64_t cap, tc_block_info *info) {
+    TC_ENTER(ctx);
+    return compress_host(ctx, text, n, false, count, rsym, cap, info);
+}
+extern "C" int tc_bwt_mtf_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *count, int16_t *rsym,
+                                     uint64_t cap, tc_block_info *info) {
+    TC_ENTER(ctx);
+    return compress_host(ctx, text, n, true, count, rsym, cap, info);
+}
+extern "C" int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_count,
+                                         int16_t *d_rsym, uint64_t cap, tc_block_info *info) {
+    TC_ENTER(ctx);
+    if (!info) return TC_E_ARG;
+    return compress_dev(ctx, d_text, n, true, d_count, d_rsym, cap, info);
+}
+
+extern "C" int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
+                                 uint64_t cap, uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out) return TC_E_ARG;
+    *n_out = 0;
+    if (R == 0) return TC_OK;
+    // N is not known up front: a first pass sizes it (TC_E_CAP with cap 0 returns the length)
+    uint32_t *d_count;
+    int16_t *d_rsym, *d_sym;
+    uint8_t *d_text;
+    TC_TRY(ws_alloc(ctx, R, &d_count));
+    TC_TRY(ws_alloc(ctx, R, &d_rsym));
+    TC_TRY(h2d(ctx, d_count, count, R));
+    TC_TRY(h2d(ctx, d_rsym, rsym, R));
+    uint64_t N = 0;
+    int rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
+    if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    if (N == 0) return TC_OK;
+    if (N >= 0xfffffffeull) return TC_E_TOOBIG;
+    TC_TRY(ws_alloc(ctx, N, &d_sym));
+    TC_TRY(ws_alloc(ctx, N, &d_text));
+    TC_TRY(rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_sym, N, &N));
+    rc = bwt_decode_i16_dev_impl(ctx, d_sym, N, d_text, N, n_out);
+    if (rc != TC_OK) return rc;
+    uint64_t m = *n_out < cap ? *n_out : cap;
+    TC_TRY(d2h(ctx, text, d_text, m));
+    TC_TRY(sync(ctx));
+    return *n_out > cap ? TC_E_CAP : TC_OK;
+}
+
+extern "C" int tc_bwt_mtf_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym,
+                                     const tc_block_info *info, uint8_t *text, uint64_t cap, uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out || !info) return TC_E_ARG;
+    *n_out = 0;
+    const uint64_t R = info->R;
+    if (R == 0) return TC_OK;
+    uint32_t *d_count;
+    int16_t *d_rsym, *d_idx, *d_sym;
+    uint8_t *d_text;
+    TC_TRY(ws_alloc(ctx, R, &d_count));
+    TC_TRY(ws_alloc(ctx, R, &d_rsym));
+    TC_TRY(h2d(ctx, d_count, count, R));
+    TC_TRY(h2d(ctx, d_rsym, rsym, R));
+    uint64_t N = 0;
+    int rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
+    if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    if (N == 0) return TC_OK;
+    if (N >= 0xfffffffeull) return TC_E_TOOBIG;
+    TC_TRY(ws_alloc(ctx, N, &d_idx));
+    TC_TRY(ws_alloc(ctx, N, &d_sym));
+    TC_TRY(ws_alloc(ctx, N, &d_text));
+    TC_TRY(rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_idx, N, &N)); // index stream: int16 == uint16 here
+    TC_TRY(mtf_decode_dev_impl(ctx, (const uint16_t *)d_idx, N, info->final_list, info->sigma, d_sym));
+    rc = bwt_decode_i16_dev_impl(ctx, d_sym, N, d_text, N, n_out);
+    if (rc != TC_OK) return rc;
+    uint64_t m = *n_out < cap ? *n_out : cap;
+    TC_TRY(d2h(ctx, text, d_text, m));
+    TC_TRY(sync(ctx));
+    return *n_out > cap ? TC_E_CAP : TC_OK;
+}

@@ -1,0 +1,178 @@
+// common.cuh -- context, scratch arena and device helpers shared by all kernels.
+// sm_100a only (B200): 148 SMs, 32-wide warps, 227 KB shared memory per CTA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/tc_b200.h"
+
+#define TC_WARP 32
+#define TC_FULL 0xffffffffu
+#define TC_NONE32 0xffffffffu
+
+struct tc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // Grow-only scratch arena: pointers handed out stay valid until the next ws_reset().
+    struct Chunk {
+        char *p;
+        size_t cap;
+    };
+    std::vector<Chunk> chunks;
+    size_t cur_off = 0;
+    size_t used_total = 0;
+    // pinned scalars for small device->host results
+    uint64_t *h_scal = nullptr; // 1024 x u64, pinned
+    uint64_t launches = 0;
+    char err[512] = {0};
+
+    int fail(cudaError_t e, const char *what, int line) {
+        snprintf(err, sizeof err, "%s at line %d: %s", what, line, cudaGetErrorString(e));
+        return TC_E_CUDA;
+    }
+};
+
+#define TC_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return ctx->fail(e_, #call, __LINE__); \
+    } while (0)
+#define TC_TRY(call)               \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != TC_OK) return rc_; \
+    } while (0)
+// kernel launch + bookkeeping
+#define TC_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+    do {                                                                      \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);      \
+        (ctx)->launches++;                                                    \
+        cudaError_t e_ = cudaPeekAtLastError();                               \
+        if (e_ != cudaSuccess) return (ctx)->fail(e_, #kernel, __LINE__);     \
+    } while (0)
+
+// ---- arena -------------------------------------------------------------------
+// ws_reset(): called at the start of a top-level op.  If the previous op spilled
+// into extra chunks, coalesce them into one chunk big enough for everything, so
+// steady state does no cudaMalloc.
+int tc_ws_reset(tc_ctx *ctx);
+int tc_ws_alloc(tc_ctx *ctx, size_t bytes, void **out);
+template <typename T>
+static inline int ws_alloc(tc_ctx *ctx, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = tc_ws_alloc(ctx, count * sizeof(T), &p);
+    *out = (T *)p;
+    return rc;
+}
+// nested ops use mark/release so a composite can reuse scratch between stages
+struct WsMark {
+    size_t nchunks, off, used;
+};
+WsMark tc_ws_mark(tc_ctx *ctx);
+void tc_ws_release(tc_ctx *ctx, WsMark m);
+
+static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// ---- internal device-level entry points (all pointers are device pointers) ----
+// radix sort of (u64 key, u32 val) pairs by the bit ranges listed (LSD, 8 bits per pass).
+// On return *out_keys/*out_vals point at whichever buffer holds the result.
+int tc_radix_sort_pairs(tc_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, uint64_t n,
+                        const int *shifts, int npass, uint64_t **out_keys, uint32_t **out_vals);
+// exclusive prefix sums (out may alias in)
+int tc_scan_exclusive_u32_to_u64(tc_ctx *ctx, const uint32_t *in, uint64_t *out, uint64_t n, uint64_t *d_total);
+int tc_scan_exclusive_u32(tc_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *d_total);
+int tc_scan_exclusive_u64(tc_ctx *ctx, const uint64_t *in, uint64_t *out, uint64_t n, uint64_t *d_total);
+int tc_scan_inclusive_max_u32(tc_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);
+// suffix array of text$ (0-based start positions, N = n+1 entries) in d_sa
+int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_sa);
+
+// ---- device helpers --------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// streaming 128-bit loads/stores that bypass L1 allocation (data touched once)
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_u4(void *p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_sum(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(TC_FULL, v, d);
+        if (lane_id() >= (unsigned)d) v += o;
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_incl_max(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(TC_FULL, v, d);
+        if (lane_id() >= (unsigned)d) v = o > v ? o : v;
+    }
+    return v;
+}
+// Block-wide exclusive sum.  `sh` needs THREADS/32 + 1 elements.  All threads must call.
+template <typename T, int THREADS>
+__device__ __forceinline__ T block_excl_sum(T v, T *sh, T *total) {
+    const int w = threadIdx.x >> 5;
+    T inc = warp_incl_sum(v);
+    if (lane_id() == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = (lane_id() < THREADS / 32) ? sh[lane_id()] : T(0);
+        T xi = warp_incl_sum(x);
+        if (lane_id() < THREADS / 32) sh[lane_id()] = xi - x;
+        if (lane_id() == 31) sh[THREADS / 32] = xi;
+    }
+    __syncthreads();
+    T r = sh[w] + inc - v;
+    if (total) *total = sh[THREADS / 32];
+    __syncthreads();
+    return r;
+}
+// Block-wide exclusive max with identity `ident` (ident must be <= every value).
+template <typename T, int THREADS>
+__device__ __forceinline__ T block_excl_max(T v, T ident, T *sh, T *total) {
+    const int w = threadIdx.x >> 5;
+    T inc = warp_incl_max(v);
+    T prev = __shfl_up_sync(TC_FULL, inc, 1);
+    if (lane_id() == 0) prev = ident;
+    if (lane_id() == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T x = (lane_id() < THREADS / 32) ? sh[lane_id()] : ident;
+        T xi = warp_incl_max(x);
+        T xe = __shfl_up_sync(TC_FULL, xi, 1);
+        if (lane_id() == 0) xe = ident;
+        if (lane_id() < THREADS / 32) sh[lane_id()] = xe;
+        if (lane_id() == 31) sh[THREADS / 32] = xi;
+    }
+    __syncthreads();
+    T base = sh[w];
+    T r = base > prev ? base : prev;
+    if (total) *total = sh[THREADS / 32];
+    __syncthreads();
+    return r;
+}
+#endif

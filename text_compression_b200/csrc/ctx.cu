@@ -1,0 +1,142 @@
+// ctx.cu -- context lifecycle, scratch arena, pinned host memory, error strings.
+#include "common.cuh"
+
+static const size_t kAlign = 512;
+
+extern "C" const char *tc_version(void) { return "text_compression_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *tc_strerror(int rc) {
+    switch (rc) {
+        case TC_OK: return "ok";
+        case TC_E_CUDA: return "CUDA runtime error (see tc_last_error)";
+        case TC_E_CAP: return "output capacity too small";
+        case TC_E_FROMJUST: return "reference semantics: fromJust Nothing";
+        case TC_E_INDEX: return "reference semantics: index out of bounds";
+        case TC_E_NOMEM: return "out of memory";
+        case TC_E_ARG: return "invalid argument";
+        case TC_E_TOOBIG: return "input too large (n must be < 2^32-2)";
+        case TC_E_NODEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    }
+    return "unknown error";
+}
+
+extern "C" const char *tc_last_error(const tc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" uint64_t tc_ctx_launches(const tc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc_ctx **out) {
+    if (!out) return TC_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return TC_E_NODEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return TC_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TC_E_NODEVICE;
+    if (prop.major < 10) return TC_E_NODEVICE; // kernels are compiled for sm_100a only
+    tc_ctx *ctx = new tc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (have_stream) {
+        ctx->stream = stream;
+        ctx->own_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return TC_E_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    if (cudaMallocHost((void **)&ctx->h_scal, 1024 * sizeof(uint64_t)) != cudaSuccess) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return TC_E_NOMEM;
+    }
+    *out = ctx;
+    return TC_OK;
+}
+
+extern "C" int tc_ctx_create(int device, tc_ctx **out) { return ctx_create_impl(device, nullptr, false, out); }
+extern "C" int tc_ctx_create_on_stream(int device, void *cuda_stream, tc_ctx **out) {
+    return ctx_create_impl(device, (cudaStream_t)cuda_stream, true, out);
+}
+
+extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &c : ctx->chunks) cudaFree(c.p);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int tc_ctx_sync(tc_ctx *ctx) {
+    if (!ctx) return TC_E_ARG;
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TC_OK;
+}
+
+extern "C" void *tc_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void tc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int tc_ws_reset(tc_ctx *ctx) {
+    TC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->chunks.size() > 1) {
+        size_t total = 0;
+        for (auto &c : ctx->chunks) total += c.cap;
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (auto &c : ctx->chunks) cudaFree(c.p);
+        ctx->chunks.clear();
+        char *p = nullptr;
+        total += total / 8;
+        if (cudaMalloc((void **)&p, total) != cudaSuccess) {
+            cudaGetLastError();
+            return TC_E_NOMEM;
+        }
+        ctx->chunks.push_back({p, total});
+    }
+    ctx->cur_off = 0;
+    ctx->used_total = 0;
+    return TC_OK;
+}
+
+int tc_ws_alloc(tc_ctx *ctx, size_t bytes, void **out) {
+    bytes = (bytes + kAlign - 1) / kAlign * kAlign;
+    if (bytes == 0) bytes = kAlign;
+    if (ctx->chunks.empty() || ctx->cur_off + bytes > ctx->chunks.back().cap) {
+        size_t cap = bytes > (size_t(64) << 20) ? bytes : (size_t(64) << 20);
+        char *p = nullptr;
+        if (cudaMalloc((void **)&p, cap) != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(ctx->err, sizeof ctx->err, "scratch arena: cudaMalloc(%zu) failed", cap);
+            return TC_E_NOMEM;
+        }
+        ctx->chunks.push_back({p, cap});
+        ctx->cur_off = 0;
+    }
+    *out = ctx->chunks.back().p + ctx->cur_off;
+    ctx->cur_off += bytes;
+    ctx->used_total += bytes;
+    return TC_OK;
+}
+
+WsMark tc_ws_mark(tc_ctx *ctx) { return WsMark{ctx->chunks.size(), ctx->cur_off, ctx->used_total}; }
+void tc_ws_release(tc_ctx *ctx, WsMark m) {
+    // Only rewind inside the chunk that was current at mark time; later chunks stay
+    // allocated (they are coalesced by the next ws_reset) but are not reused before then.
+    if (ctx->chunks.size() == m.nchunks) {
+        ctx->cur_off = m.off;
+        ctx->used_total = m.used;
+    }
+}

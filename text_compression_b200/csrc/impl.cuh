@@ -1,0 +1,29 @@
+// impl.cuh -- device-level implementations (all data pointers are DEVICE pointers; scalar
+// results come back through host pointers after a stream sync).  None of these resets the
+// scratch arena: only the extern "C" entry points in api.cu do, once per top-level call.
+#pragma once
+#include "common.cuh"
+
+int bwt_encode_dev_impl(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t *d_bwt, uint64_t *primary,
+                        uint32_t *d_sa_1based);
+int bwt_decode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint8_t *d_text,
+                           uint64_t cap, uint64_t *n_out);
+int bwt_decode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_bwt, uint64_t N, uint8_t *d_text, uint64_t cap,
+                            uint64_t *n_out);
+int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
+                           int16_t *final_list, uint32_t *sigma);
+int mtf_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint16_t *d_idx, int16_t *final_list,
+                            uint32_t *sigma);
+int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const int16_t *final_list, uint32_t sigma_in,
+                        int16_t *d_sym);
+int rle_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint32_t *d_count,
+                           int16_t *d_rsym, uint64_t cap, uint64_t *R);
+int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
+                            uint64_t cap, uint64_t *R);
+int rle_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
+                            uint64_t cap, uint64_t *R);
+int rle_decode_dev_impl(tc_ctx *ctx, const uint32_t *d_count, const int16_t *d_rsym, uint64_t R, int16_t *d_sym,
+                        uint64_t cap, uint64_t *N_out);
+int tc_byte_hist_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *h_hist);
+int tc_bwt_emit_dev(tc_ctx *ctx, const uint8_t *d_text, const uint32_t *d_sa, uint64_t N, uint8_t *d_bwt,
+                    uint64_t *primary);

@@ -1,0 +1,356 @@
+// rle.cu -- seqToRLE / seqFromRLE (src/Data/RLE/Internal.hs:104-189) as
+// flag -> scan -> compaction kernels with 128-bit coalesced HBM access.
+//
+// Position-local form of the reference's sequential state machine:
+//   head(i)  : x[i] is Just and (i == 0 or x[i-1] is Nothing or x[i-1] != x[i])
+//   H(i)     : latest head <= i            (max-scan)
+//   J(i)     : latest Just position <= i   (max-scan)
+//   at i >= 1:  x[i] Nothing            -> 2 pairs: state(i), (1, Nothing)
+//               x[i], x[i-1] Just, !=   -> 1 pair : (i - H(i-1), x[i-1])
+//   state(i) = x[i-1] Just ? (i - H(i-1), x[i-1]) : (stale, Nothing),
+//              stale = J(i-1) - H(i-1) + 1, or 1 when no Just precedes (Q1-Q3)
+//   after the last position: one pair state(N).
+// Algorithmic bytes: N * w_in read + 6 * R written (u32 count + i16 symbol per run).
+#include "common.cuh"
+#include "impl.cuh"
+
+namespace {
+constexpr int RT = 256;
+constexpr int NOPREV = -2;
+
+struct InU8 {
+    const uint8_t *p;
+    uint64_t primary;
+    static constexpr int ITEMS = 16;
+    static constexpr int MAX_PER_ITEM = 1; // a single Nothing: at most TILE + 1 pairs + the flush
+    __device__ __forceinline__ int at(uint64_t i) const { return i == primary ? -1 : (int)p[i]; }
+    __device__ __forceinline__ void load(uint64_t base, uint64_t N, int *c) const {
+        if (base + ITEMS <= N && ((reinterpret_cast<uintptr_t>(p + base) & 15) == 0)) {
+            uint4 v = ld_stream_u4(p + base);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 16; k++) c[k] = (w[k >> 2] >> ((k & 3) * 8)) & 0xff;
+            if (primary >= base && primary < base + ITEMS) {
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if (base + k == primary) c[k] = -1;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) c[k] = (base + k < N) ? at(base + k) : 0;
+        }
+    }
+};
+template <bool SIGNED>
+struct In16 {
+    const uint16_t *p;
+    static constexpr int ITEMS = SIGNED ? 8 : 16;
+    static constexpr int MAX_PER_ITEM = SIGNED ? 2 : 1; // every position may be a Nothing (2 pairs)
+    __device__ __forceinline__ int cvt(uint32_t h) const {
+        if (SIGNED) {
+            int v = (int)(int16_t)h;
+            return v < 0 ? -1 : v;
+        }
+        return (int)h;
+    }
+    __device__ __forceinline__ int at(uint64_t i) const { return cvt(p[i]); }
+    __device__ __forceinline__ void load(uint64_t base, uint64_t N, int *c) const {
+        if (base + ITEMS <= N && ((reinterpret_cast<uintptr_t>(p + base) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < ITEMS / 8; q++) {
+                uint4 v = ld_stream_u4(p + base + q * 8);
+                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) c[q * 8 + k] = cvt((w[k >> 1] >> ((k & 1) * 16)) & 0xffff);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) c[k] = (base + k < N) ? at(base + k) : 0;
+        }
+    }
+};
+
+// emissions of position i given its symbol c and predecessor p (NOPREV at i == 0)
+__device__ __forceinline__ int n_emit(int c, int p) {
+    if (p == NOPREV) return 0;
+    if (c < 0) return 2;
+    return (p >= 0 && p != c) ? 1 : 0;
+}
+
+template <class In>
+__global__ void __launch_bounds__(RT)
+    rle_reduce_kernel(In in, uint64_t N, uint32_t *__restrict__ tile_pairs, uint32_t *__restrict__ tile_head,
+                      uint32_t *__restrict__ tile_just) {
+    constexpr int ITEMS = In::ITEMS;
+    __shared__ uint32_t sh[RT / 32 + 1];
+    uint64_t base = ((uint64_t)blockIdx.x * RT + threadIdx.x) * ITEMS;
+    int c[ITEMS];
+    uint32_t pairs = 0, lh = 0, lj = 0;
+    if (base < N) {
+        in.load(base, N, c);
+        int p = base == 0 ? NOPREV : in.at(base - 1);
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            uint64_t i = base + k;
+            if (i < N) {
+                pairs += n_emit(c[k], p);
+                if (c[k] >= 0) {
+                    lj = (uint32_t)i + 1;
+                    if (p < 0 || p != c[k]) lh = (uint32_t)i + 1;
+                }
+                p = c[k];
+            }
+        }
+    }
+    uint32_t tp, th, tj;
+    block_excl_sum<uint32_t, RT>(pairs, sh, &tp);
+    block_excl_max<uint32_t, RT>(lh, 0u, sh, &th);
+    block_excl_max<uint32_t, RT>(lj, 0u, sh, &tj);
+    if (threadIdx.x == 0) {
+        tile_pairs[blockIdx.x] = tp;
+        tile_head[blockIdx.x] = th;
+        tile_just[blockIdx.x] = tj;
+    }
+}
+
+// single block: exclusive sum of pairs (u64) and exclusive max of head / just over tiles
+__global__ void __launch_bounds__(1024)
+    rle_tile_scan_kernel(const uint32_t *__restrict__ tile_pairs, uint32_t *tile_head, uint32_t *tile_just,
+                         uint64_t *__restrict__ tile_off, uint64_t tiles) {
+    __shared__ uint64_t sh64[1024 / 32 + 1];
+    __shared__ uint32_t sh32[1024 / 32 + 1];
+    uint64_t carry = 0;
+    uint32_t ch = 0, cj = 0;
+    for (uint64_t b = 0; b < tiles; b += 1024) {
+        uint64_t t = b + threadIdx.x;
+        uint64_t v = t < tiles ? tile_pairs[t] : 0;
+        uint32_t h = t < tiles ? tile_head[t] : 0;
+        uint32_t j = t < tiles ? tile_just[t] : 0;
+        uint64_t tot;
+        uint32_t th, tj;
+        uint64_t ex = block_excl_sum<uint64_t, 1024>(v, sh64, &tot);
+        uint32_t hx = block_excl_max<uint32_t, 1024>(h, 0u, sh32, &th);
+        uint32_t jx = block_excl_max<uint32_t, 1024>(j, 0u, sh32, &tj);
+        if (t < tiles) {
+            tile_off[t] = carry + ex;
+            tile_head[t] = max(ch, hx);
+            tile_just[t] = max(cj, jx);
+        }
+        carry += tot;
+        ch = max(ch, th);
+        cj = max(cj, tj);
+    }
+}
+
+template <class In>
+__global__ void __launch_bounds__(RT)
+    rle_emit_kernel(In in, uint64_t N, const uint64_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_headx,
+                    const uint32_t *__restrict__ tile_justx, uint32_t *__restrict__ count, int16_t *__restrict__ rsym,
+                    uint64_t cap, uint64_t *__restrict__ d_R) {
+    constexpr int ITEMS = In::ITEMS;
+    constexpr int CAP = In::MAX_PER_ITEM * RT * ITEMS + 3; // + one Nothing's second pair + final flush
+    __shared__ uint32_t sh[RT / 32 + 1];
+    __shared__ uint32_t s_cnt[CAP];
+    __shared__ int16_t s_sym[CAP];
+    uint64_t base = ((uint64_t)blockIdx.x * RT + threadIdx.x) * ITEMS;
+    int c[ITEMS];
+    int p0 = NOPREV;
+    uint32_t pairs = 0, lh = 0, lj = 0;
+    if (base < N) {
+        in.load(base, N, c);
+        p0 = base == 0 ? NOPREV : in.at(base - 1);
+        int p = p0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            uint64_t i = base + k;
+            if (i < N) {
+                pairs += n_emit(c[k], p);
+                if (c[k] >= 0) {
+                    lj = (uint32_t)i + 1;
+                    if (p < 0 || p != c[k]) lh = (uint32_t)i + 1;
+                }
+                p = c[k];
+            }
+        }
+        if (base + ITEMS >= N) pairs += 1; // this thread owns position N-1: final flush
+    }
+    uint32_t tile_total;
+    uint32_t o = block_excl_sum<uint32_t, RT>(pairs, sh, &tile_total);
+    uint32_t H = block_excl_max<uint32_t, RT>(lh, 0u, sh, (uint32_t *)nullptr);
+    uint32_t J = block_excl_max<uint32_t, RT>(lj, 0u, sh, (uint32_t *)nullptr);
+    H = max(H, tile_headx[blockIdx.x]);
+    J = max(J, tile_justx[blockIdx.x]);
+    if (base < N) {
+        int p = p0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; k++) {
+            uint64_t i = base + k;
+            if (i < N) {
+                int ck = c[k];
+                if (p != NOPREV) {
+                    if (ck < 0) {
+                        if (p >= 0) {
+                            s_cnt[o] = (uint32_t)i - (H - 1);
+                            s_sym[o] = (int16_t)p;
+                        } else {
+                            s_cnt[o] = J == 0 ? 1u : J - H + 1;
+                            s_sym[o] = -1;
+                        }
+                        s_cnt[o + 1] = 1;
+                        s_sym[o + 1] = -1;
+                        o += 2;
+                    } else if (p >= 0 && p != ck) {
+                        s_cnt[o] = (uint32_t)i - (H - 1);
+                        s_sym[o] = (int16_t)p;
+                        o += 1;
+                    }
+                }
+                if (ck >= 0) {
+                    J = (uint32_t)i + 1;
+                    if (p < 0 || p != ck) H = (uint32_t)i + 1;
+                }
+                if (i == N - 1) { // end-of-input flush (src/Data/RLE/Internal.hs:125-130)
+                    if (ck >= 0) {
+                        s_cnt[o] = (uint32_t)N - (H - 1);
+                        s_sym[o] = (int16_t)ck;
+                    } else {
+                        s_cnt[o] = J == 0 ? 1u : J - H + 1;
+                        s_sym[o] = -1;
+                    }
+                    o += 1;
+                }
+                p = ck;
+            }
+        }
+    }
+    __syncthreads();
+    uint64_t goff = tile_off[blockIdx.x];
+    for (uint32_t j = threadIdx.x; j < tile_total; j += RT) {
+        uint64_t g = goff + j;
+        if (g < cap) {
+            count[g] = s_cnt[j];
+            rsym[g] = s_sym[j];
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;
+}
+
+template <class In>
+int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *d_rsym, uint64_t cap, uint64_t *R) {
+    *R = 0;
+    if (N == 0) return TC_OK;
+    if (N >= 0xfffffffeull) return TC_E_TOOBIG;
+    constexpr uint64_t TILE = (uint64_t)RT * In::ITEMS;
+    uint64_t tiles = ceil_div_u64(N, TILE);
+    WsMark mk = tc_ws_mark(ctx);
+    uint32_t *tp, *th, *tj;
+    uint64_t *toff, *d_R;
+    TC_TRY(ws_alloc(ctx, tiles, &tp));
+    TC_TRY(ws_alloc(ctx, tiles, &th));
+    TC_TRY(ws_alloc(ctx, tiles, &tj));
+    TC_TRY(ws_alloc(ctx, tiles, &toff));
+    TC_TRY(ws_alloc(ctx, 1, &d_R));
+    TC_LAUNCH(ctx, (rle_reduce_kernel<In>), (unsigned)tiles, RT, 0, in, N, tp, th, tj);
+    // NB: the reduce kernel's tile pair counts exclude the final flush; the emit kernel adds it
+    // for the owner of position N-1, which is always in the last tile, so offsets stay exact.
+    TC_LAUNCH(ctx, rle_tile_scan_kernel, 1, 1024, 0, tp, th, tj, toff, tiles);
+    TC_LAUNCH(ctx, (rle_emit_kernel<In>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap, d_R);
+    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_R, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *R = ctx->h_scal[0];
+    tc_ws_release(ctx, mk);
+    return *R > cap ? TC_E_CAP : TC_OK;
+}
+
+// ---- decode ------------------------------------------------------------------
+__global__ void rle_len_kernel(const uint32_t *__restrict__ count, const int16_t *__restrict__ rsym, uint64_t R,
+                               uint32_t *__restrict__ len) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < R) len[k] = rsym[k] < 0 ? 1u : count[k]; // (Just _, Nothing) -> one Nothing, count ignored
+}
+
+constexpr int DT = 256;
+constexpr int DITEMS = 8;
+__global__ void __launch_bounds__(DT)
+    rle_expand_kernel(const uint64_t *__restrict__ off, const int16_t *__restrict__ rsym, uint64_t R,
+                      const uint64_t *__restrict__ d_total, int16_t *__restrict__ out, uint64_t cap) {
+    uint64_t total = *d_total;
+    uint64_t lim = total < cap ? total : cap;
+    uint64_t o0 = ((uint64_t)blockIdx.x * DT + threadIdx.x) * DITEMS;
+    if (o0 >= lim) return;
+    // last k with off[k] <= o0
+    uint64_t lo = 0, hi = R; // invariant: off[lo] <= o0, (hi == R or off[hi] > o0)
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (off[mid] <= o0) lo = mid; else hi = mid;
+    }
+    uint64_t k = lo;
+    uint64_t end = (k + 1 < R) ? off[k + 1] : total;
+    int16_t s = rsym[k];
+    int16_t v[DITEMS];
+#pragma unroll
+    for (int j = 0; j < DITEMS; j++) {
+        uint64_t o = o0 + j;
+        if (o < lim) {
+            while (o >= end) {
+                k++;
+                end = (k + 1 < R) ? off[k + 1] : total;
+                s = rsym[k];
+            }
+        }
+        v[j] = s;
+    }
+    if (o0 + DITEMS <= lim && ((reinterpret_cast<uintptr_t>(out + o0) & 15) == 0)) {
+        uint4 w;
+        w.x = (uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+        w.y = (uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+        w.z = (uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+        w.w = (uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+        st_stream_u4(out + o0, w);
+    } else {
+#pragma unroll
+        for (int j = 0; j < DITEMS; j++)
+            if (o0 + j < lim) out[o0 + j] = v[j];
+    }
+}
+} // namespace
+
+// internal: device pointers
+int rle_decode_dev_impl(tc_ctx *ctx, const uint32_t *d_count, const int16_t *d_rsym, uint64_t R, int16_t *d_sym,
+                           uint64_t cap, uint64_t *N_out) {
+    *N_out = 0;
+    if (R == 0) return TC_OK;
+    WsMark mk = tc_ws_mark(ctx);
+    uint32_t *len;
+    uint64_t *off, *d_total;
+    TC_TRY(ws_alloc(ctx, R, &len));
+    TC_TRY(ws_alloc(ctx, R, &off));
+    TC_TRY(ws_alloc(ctx, 1, &d_total));
+    TC_LAUNCH(ctx, rle_len_kernel, (unsigned)ceil_div_u64(R, 256), 256, 0, d_count, d_rsym, R, len);
+    TC_TRY(tc_scan_exclusive_u32_to_u64(ctx, len, off, R, d_total));
+    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t total = ctx->h_scal[0];
+    *N_out = total;
+    uint64_t lim = total < cap ? total : cap;
+    if (lim > 0) {
+        uint64_t blocks = ceil_div_u64(lim, (uint64_t)DT * DITEMS);
+        TC_LAUNCH(ctx, rle_expand_kernel, (unsigned)blocks, DT, 0, off, d_rsym, R, d_total, d_sym, cap);
+    }
+    tc_ws_release(ctx, mk);
+    return total > cap ? TC_E_CAP : TC_OK;
+}
+
+int rle_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint32_t *d_count,
+                           int16_t *d_rsym, uint64_t cap, uint64_t *R) {
+    if (N && primary >= N) primary = ~0ull; // no Nothing in range: plain byte stream
+    return rle_encode_impl(ctx, InU8{d_bwt, primary}, N, d_count, d_rsym, cap, R);
+}
+int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
+                            uint64_t cap, uint64_t *R) {
+    return rle_encode_impl(ctx, In16<false>{d_idx}, N, d_count, d_rsym, cap, R);
+}
+int rle_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
+                               uint64_t cap, uint64_t *R) {
+    return rle_encode_impl(ctx, In16<true>{(const uint16_t *)d_sym}, N, d_count, d_rsym, cap, R);
+}
