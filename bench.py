@@ -1,0 +1,391 @@
+#!/usr/bin/env python3
+"""bench.py -- BWT+MTF+RLE throughput (and FM-index count queries/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference
+
+A step = one pass of the hot path over one 16 MiB block of synthetic random bytes per GPU
+(BASELINE.json configs[1]; the multi-block config 5 partitions such blocks over the GPUs, so
+N GPUs process N blocks per step with no data-path collective: weak scaling).
+
+Timed region of `value`: inputs already resident in HBM, CUDA events on the launching stream,
+barrier + synchronize on both sides, max over ranks.  `e2e` is the same metric through the
+host-buffer C-ABI call (tc_bwt_mtf_rle_encode) with H2D of the text and D2H of the runs inside
+the timed region.  Inputs rotate over 12 distinct blocks (192 MiB > the 126 MB L2) and every
+step streams ~4 GB through HBM, so nothing is L2-resident between steps.
+
+The reference is Haskell and no GHC exists in the image (probed on the GPU box too), so the
+reference arm and `cpu_baseline` time oracle/tc_oracle.c, the C restatement of the reference
+algorithm ("port"), on the box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 16 << 20
+NBLOCKS = 12
+METRIC = "bwt_mtf_rle_MB_per_s"
+WORKLOAD = "C2: BWT+MTF+RLE of one 16 MiB synthetic random-byte block per GPU per step"
+CPU_SAMPLE = 1 << 20
+
+
+def gen_block(seed: int, n: int) -> np.ndarray:
+    from tests.util import gen_bytes
+    return gen_bytes(seed, n)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 7 and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_time(text: np.ndarray):
+    """One pass of the oracle (C restatement of the reference algorithm) over `text`."""
+    from oracle import oracle as orc
+    t0 = time.perf_counter()
+    bwt = orc.bwt_encode(text)
+    idx, fin = orc.mtf_encode(bwt)
+    cnt, sym = orc.rle_encode(idx.astype(np.int16))
+    return time.perf_counter() - t0, int(cnt.size)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own (sequential) CPU algorithm, restated in C."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = gen_block(0xC2, BLOCK)[:CPU_SAMPLE]
+    for _ in range(args.warmup):
+        cpu_port_time(sample[: CPU_SAMPLE // 8])
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_port_time(sample)
+        t += dt
+    val = args.steps * sample.size / 1e6 / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "block_bytes": BLOCK, "sample_bytes": int(sample.size)},
+        "cpu_baseline": {"value": val, "unit": "MB/s", "cores": 1, "kind": "port",
+                         "sample": f"first {sample.size >> 20} MiB of the seed-0xC2 block per step; C restatement of the "
+                                   "reference (comparison suffix sort, list MTF, sequential RLE), single thread like the "
+                                   "reference's toBWT/seqToMTF/seqToRLE; Haskell original not buildable (no GHC)"},
+        "e2e": {"value": val, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from text_compression_b200 import _lib
+    from text_compression_b200._lib import BlockInfo, ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: text_compression_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    ctx = _lib.Context(local, stream.cuda_stream)
+    n = BLOCK
+
+    # ---- inputs: NBLOCKS distinct blocks per rank, resident in HBM, plus pinned host copies
+    host_blocks = [gen_block(0xC2 + 1000 * rank + b, n) for b in range(NBLOCKS)]
+    d_text = torch.empty((NBLOCKS, n), dtype=torch.uint8, device="cuda")
+    for b in range(NBLOCKS):
+        d_text[b].copy_(torch.from_numpy(host_blocks[b]))
+    cap = n + 3
+    d_count = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_rsym = torch.empty(cap, dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    info = BlockInfo()
+
+    def step_dev(i):
+        b = i % NBLOCKS
+        ctx.call("tc_bwt_mtf_rle_encode_dev", C.c_void_p(d_text[b].data_ptr()), n, C.c_void_p(d_count.data_ptr()),
+                 C.c_void_p(d_rsym.data_ptr()), cap, C.byref(info))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_dev(i)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = ctx.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(args.steps):
+            step_dev(args.warmup + i)
+        ev1.record(stream)
+        barrier()
+        launches = ctx.launches - launches0
+        sampler.stop_flag.set()
+        sampler.join()
+        ms = ev0.elapsed_time(ev1)
+        R_last = int(info.R)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        value = world * args.steps * n / 1e6 / (ms / 1e3)
+
+        # ---- e2e: host buffers through the C-ABI call, H2D + D2H inside the timed region
+        h_in = [_lib.pinned_empty(n, np.uint8) for _ in range(2)]
+        h_cnt = _lib.pinned_empty(cap, np.uint32)
+        h_sym = _lib.pinned_empty(cap, np.int16)
+        einfo = BlockInfo()
+
+        def step_host(i):
+            ctx.call("tc_bwt_mtf_rle_encode", ptr(h_in[i % 2]), n, ptr(h_cnt), ptr(h_sym), cap, C.byref(einfo))
+
+        h_in[0][:] = host_blocks[0]
+        h_in[1][:] = host_blocks[1]
+        for i in range(max(1, min(args.warmup, 2))):
+            step_host(i)
+        barrier()
+        e_steps = args.steps
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            step_host(i)
+        torch.cuda.synchronize()
+        e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t.item())
+        e2e_val = world * e_steps * n / 1e6 / e_s
+        d2h = int(einfo.R) * 6
+
+        # ---- per-kernel timing (CUDA events around every launch) for the roofline
+        barrier()
+        ctx.profile(True)
+        PSTEPS = 2
+        for i in range(PSTEPS):
+            step_dev(i)
+        prof = ctx.profile_report()
+        ctx.profile(False)
+
+    peak, peak_src = peaks()
+    tot_ms = sum(v[1] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    tname, (tn, tms, tbytes) = top
+    roofline = {"bound": "hbm", "kernel": tname, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                "traffic": None, "launches_per_step": tn / PSTEPS, "avg_launch_us": 1e3 * tms / tn,
+                "share_of_kernel_time": tms / tot_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": tbytes / tn if tn else None}
+    if tbytes:
+        roofline["achieved"] = tbytes / 1e9 / (tms / 1e3)
+        roofline["frac"] = roofline["achieved"] / peak
+    N = n + 1
+
+    def pass_ms(prefixes):
+        return sum(v[1] for k, v in prof.items() if k.split("<")[0].strip().startswith(prefixes)) / PSTEPS
+
+    mtf_ms = pass_ms(("mtf_",))
+    rle_ms = pass_ms(("rle_",))
+    bwt_ms = tot_ms / PSTEPS - mtf_ms - rle_ms
+    mtf_bytes = N * 3                     # u8 symbol in, u16 index out (sigma = 257)
+    rle_bytes = N * 2 + 6 * R_last        # u16 index in, (u32 count, i16 symbol) per run out
+    passes = {
+        "bwt": {"ms": bwt_ms},
+        "mtf": {"ms": mtf_ms, "GBps": mtf_bytes / 1e9 / (mtf_ms / 1e3), "frac": mtf_bytes / 1e9 / (mtf_ms / 1e3) / peak},
+        "rle": {"ms": rle_ms, "GBps": rle_bytes / 1e9 / (rle_ms / 1e3), "frac": rle_bytes / 1e9 / (rle_ms / 1e3) / peak},
+        "kernel_ms_per_step": {k: v[1] / PSTEPS for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+
+    line = None
+    if rank == 0:
+        cpu_s, _ = cpu_port_time(host_blocks[0][:CPU_SAMPLE])
+        line = {
+            "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "block_bytes": n, "blocks_per_step": world, "sigma": int(info.sigma),
+                       "runs_per_block": R_last,
+                       "l2": f"inputs rotate over {NBLOCKS} distinct blocks ({NBLOCKS * n >> 20} MiB > L2); "
+                             "each step streams > 1 GB of sort traffic"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_val, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
+                    "api": "tc_bwt_mtf_rle_encode (host buffers, pinned)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "passes": passes,
+            "cpu_baseline": {"value": CPU_SAMPLE / 1e6 / cpu_s, "unit": "MB/s", "cores": 1, "kind": "port",
+                             "sample": f"first {CPU_SAMPLE >> 20} MiB of block 0, one pass; C restatement of the "
+                                       "reference algorithm, single thread (the reference path is sequential)"},
+        }
+    if args.fm and world >= 1:
+        fm = run_fm(args, ctx, stream, world, rank, local, peak)
+        if line is not None:
+            line["fm_count"] = fm
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_fm(args, ctx, stream, world, rank, local, peak):
+    """Config 3: toFMIndex on synthetic ACGTN + countFMIndex for 100-bp reads, queries sharded
+    over the GPUs, index built on rank 0 and replicated with one NCCL broadcast."""
+    import torch
+    import torch.distributed as dist
+    from text_compression_b200 import multi
+    from text_compression_b200._lib import FmInfo
+    n, q, m = args.fm_n, args.fm_q, 100
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0xC3)
+    with torch.cuda.stream(stream):
+        r = torch.rand(n, device="cuda", generator=g)
+        base = torch.randint(0, 4, (n,), device="cuda", generator=g)
+        lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+        text = torch.where(r < 0.01, torch.tensor(ord("N"), dtype=torch.uint8, device="cuda"), lut[base])
+        del r, base
+        t0 = time.perf_counter()
+        fm = multi.build_replicated(ctx, text, n, args.fm_rate)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        # reads: substrings at uniform offsets, 10 % with one random substitution
+        q_local = q // world
+        g.manual_seed(0xC3 + 1 + rank)
+        offs = torch.randint(0, n - m, (q_local,), device="cuda", generator=g)
+        reads = text[offs[:, None] + torch.arange(m, device="cuda")[None, :]].contiguous()
+        mut = torch.rand(q_local, device="cuda", generator=g) < 0.10
+        pos = torch.randint(0, m, (q_local,), device="cuda", generator=g)
+        sub = lut[torch.randint(0, 4, (q_local,), device="cuda", generator=g)]
+        rows = torch.nonzero(mut).squeeze(1)
+        reads[rows, pos[rows]] = sub[rows]
+        off = (torch.arange(q_local + 1, device="cuda", dtype=torch.int64) * m).contiguous()
+        counts = torch.empty(q_local, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+
+        def once():
+            ctx.call("tc_fm_count_dev", fm.h, C.c_void_p(reads.data_ptr()), C.c_void_p(off.data_ptr()), q_local,
+                     C.c_void_p(counts.data_ptr()))
+
+        for _ in range(max(3, args.warmup)):
+            once()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            once()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        found = int((counts >= 0).sum().item())
+    qps = world * q_local * args.steps / (ms / 1e3)
+    per_query = m + 8 + 2 * (m - 1) * 32
+    out = {"metric": "fm_count_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world,
+           "config": {"workload": f"C3: toFMIndex on {n} bp synthetic ACGTN + countFMIndex, {q_local * world} reads x {m} bp, "
+                                  "queries sharded over GPUs, index replicated by NCCL broadcast",
+                      "sa_sample_rate": args.fm_rate},
+           "build_s": build_s, "ms_per_batch": ms / args.steps, "found_frac": found / max(q_local, 1),
+           "roofline": {"bound": "hbm", "achieved": qps / world * per_query / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": qps / world * per_query / 1e9 / peak, "bytes_per_query": per_query,
+                        "note": "algorithmic sector bytes; the 100 Mbp index (~85 MB) mostly lives in L2"},
+           "index_bytes": int(fm.info.blob_bytes)}
+    if rank == 0:
+        # CPU baseline on a bounded sample: checkpointed-Occ restatement, all host threads
+        from oracle import oracle as orc
+        ns, qs = min(n, 4_000_000), min(q_local, 200_000)
+        th = text[:ns].cpu().numpy()
+        ofm = orc.FMIndexSampled(th)
+        rd = reads[:qs].cpu().numpy()
+        flat = np.ascontiguousarray(rd.reshape(-1))
+        offh = (np.arange(qs + 1, dtype=np.uint64) * m)
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        ofm.count_batch(flat, offh, cores)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": qs / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+                               "sample": f"{qs} reads against the first {ns} bp (index build not timed); pthreads over "
+                                         "contiguous chunks like parListChunk; checkpointed Occ instead of the "
+                                         "reference's dense sigma x N table"}
+    fm.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fm", type=int, default=1, help="also run the FM-index count workload (config 3)")
+    ap.add_argument("--fm-n", type=int, default=100_000_000)
+    ap.add_argument("--fm-q", type=int, default=10_000_000)
+    ap.add_argument("--fm-rate", type=int, default=32)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

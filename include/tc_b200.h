@@ -63,6 +63,10 @@ void tc_host_free(void *p);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t tc_ctx_launches(const tc_ctx *ctx);
 const char *tc_version(void);
+/* Per-kernel device timing for bench.py's roofline: on != 0 records one CUDA-event pair per
+ * launch on the context's stream; the report is "name\tlaunches\ttotal_ms\n" lines. */
+int tc_ctx_profile(tc_ctx *ctx, int on);
+int tc_ctx_profile_report(tc_ctx *ctx, char *buf, size_t cap);
 
 /* ---- Data.BWT -------------------------------------------------------------- */
 /* createSuffixArray + saToBWT + toBWT (src/Data/BWT/Internal.hs:98-134,

@@ -62,6 +62,8 @@ _SIGS = {
     "tc_host_free": (None, [_vp]),
     "tc_ctx_launches": (_u64, [_vp]),
     "tc_version": (C.c_char_p, []),
+    "tc_ctx_profile": (_int, [_vp, _int]),
+    "tc_ctx_profile_report": (_int, [_vp, C.c_char_p, C.c_size_t]),
     "tc_bwt_encode": (_int, [_vp, _vp, _u64, _vp, _pu64, _vp]),
     "tc_bwt_decode": (_int, [_vp, _vp, _u64, _vp, _u64, _pu64]),
     "tc_bwt_decode_u8": (_int, [_vp, _vp, _u64, _u64, _vp, _u64, _pu64]),
@@ -162,6 +164,19 @@ class Context:
 
     def sync(self):
         self.call("tc_ctx_sync")
+
+    def profile(self, on: bool):
+        self.call("tc_ctx_profile", 1 if on else 0)
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total_ms, algorithmic_bytes)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.call("tc_ctx_profile_report", buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms, nbytes = line.split("\t")
+            out[name.strip("()")] = (int(n), float(ms), int(nbytes))
+        return out
 
     @property
     def launches(self) -> int:

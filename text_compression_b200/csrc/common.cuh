@@ -31,6 +31,24 @@ struct tc_ctx {
     uint64_t *h_scal = nullptr; // 1024 x u64, pinned
     uint64_t launches = 0;
     char err[512] = {0};
+    // optional per-kernel timing (tc_ctx_profile): one event pair per launch
+    struct ProfRec {
+        const char *name;
+        cudaEvent_t a, b;
+        uint64_t bytes; // algorithmic bytes of this launch (0 if the caller did not say)
+    };
+    bool prof_on = false;
+    uint64_t prof_bytes_next = 0;
+    std::vector<ProfRec> prof;
+    void prof_begin(const char *name) {
+        ProfRec r{name, nullptr, nullptr, prof_bytes_next};
+        prof_bytes_next = 0;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream);
+        prof.push_back(r);
+    }
+    void prof_end() { cudaEventRecord(prof.back().b, stream); }
 
     int fail(cudaError_t e, const char *what, int line) {
         snprintf(err, sizeof err, "%s at line %d: %s", what, line, cudaGetErrorString(e));
@@ -51,7 +69,9 @@ struct tc_ctx {
 // kernel launch + bookkeeping
 #define TC_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
     do {                                                                      \
+        if ((ctx)->prof_on) (ctx)->prof_begin(#kernel);                       \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);      \
+        if ((ctx)->prof_on) (ctx)->prof_end();                                \
         (ctx)->launches++;                                                    \
         cudaError_t e_ = cudaPeekAtLastError();                               \
         if (e_ != cudaSuccess) return (ctx)->fail(e_, #kernel, __LINE__);     \

@@ -72,6 +72,56 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
     delete ctx;
 }
 
+// Per-kernel device timing: on != 0 starts recording one CUDA-event pair per launch on the
+// context's stream; tc_ctx_profile_report syncs and writes "name\tlaunches\ttotal_ms\n" lines.
+extern "C" int tc_ctx_profile(tc_ctx *ctx, int on) {
+    if (!ctx) return TC_E_ARG;
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    ctx->prof_on = on != 0;
+    return TC_OK;
+}
+extern "C" int tc_ctx_profile_report(tc_ctx *ctx, char *buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return TC_E_ARG;
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    struct Agg {
+        const char *name;
+        uint64_t n;
+        double ms;
+        uint64_t bytes;
+    };
+    std::vector<Agg> agg;
+    for (auto &r : ctx->prof) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        bool found = false;
+        for (auto &a : agg)
+            if (a.name == r.name || strcmp(a.name, r.name) == 0) {
+                a.n++;
+                a.ms += ms;
+                a.bytes += r.bytes;
+                found = true;
+                break;
+            }
+        if (!found) agg.push_back({r.name, 1, ms, r.bytes});
+    }
+    size_t o = 0;
+    buf[0] = 0;
+    for (auto &a : agg) {
+        int w = snprintf(buf + o, cap - o, "%s\t%llu\t%.6f\t%llu\n", a.name, (unsigned long long)a.n, a.ms,
+                         (unsigned long long)a.bytes);
+        if (w < 0 || (size_t)w >= cap - o) break;
+        o += (size_t)w;
+    }
+    return TC_OK;
+}
+
 extern "C" int tc_ctx_sync(tc_ctx *ctx) {
     if (!ctx) return TC_E_ARG;
     TC_CUDA(cudaStreamSynchronize(ctx->stream));

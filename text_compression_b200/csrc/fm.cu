@@ -277,6 +277,18 @@ struct tc_fm {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static int fm_fill_image(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, const CodeLut &lut,
+                         uint32_t nplanes, uint64_t nblocks, RankBlock *d_planes, const uint32_t *d_sa, uint32_t rate,
+                         RankBlock *d_mark, uint32_t *d_samples) {
+    const unsigned gridB = (unsigned)ceil_div_u64(nblocks, 8);
+    TC_LAUNCH(ctx, fm_planes_kernel, gridB, 256, 0, d_bwt, N, primary, lut, nplanes, nblocks, d_planes);
+    if (nplanes) TC_LAUNCH(ctx, fm_plane_scan_kernel, nplanes, 1024, 0, d_planes, nblocks, (uint32_t *)nullptr);
+    TC_LAUNCH(ctx, fm_mark_kernel, gridB, 256, 0, d_sa, N, rate, nblocks, d_mark);
+    TC_LAUNCH(ctx, fm_plane_scan_kernel, 1, 1024, 0, d_mark, nblocks, (uint32_t *)nullptr);
+    TC_LAUNCH(ctx, fm_samples_kernel, (unsigned)ceil_div_u64(N, 256), 256, 0, d_sa, N, rate, d_mark, d_samples);
+    return TC_OK;
+}
+
 static int fm_build_dev_impl(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t rate, tc_fm **out) {
     *out = nullptr;
     if (n == 0) return TC_E_ARG; // undefined in the reference; callers guard empty input
@@ -351,17 +363,9 @@ static int fm_build_dev_impl(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uin
         h.primary = primary;
         CodeLut lut;
         memcpy(lut.code, h.code, sizeof lut.code);
-        const unsigned gridB = (unsigned)ceil_div_u64(h.nblocks, 8);
-        fm_planes_kernel<<<gridB, 256, 0, ctx->stream>>>(d_bwt, N, primary, lut, nplanes, h.nblocks, d_planes);
-        ctx->launches++;
-        if (nplanes) {
-            fm_plane_scan_kernel<<<nplanes, 1024, 0, ctx->stream>>>(d_planes, h.nblocks, nullptr);
-            ctx->launches++;
-        }
-        fm_mark_kernel<<<gridB, 256, 0, ctx->stream>>>(d_sa, N, rate, h.nblocks, d_mark);
-        fm_plane_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_mark, h.nblocks, nullptr);
-        fm_samples_kernel<<<(unsigned)ceil_div_u64(N, 256), 256, 0, ctx->stream>>>(d_sa, N, rate, d_mark, d_samples);
-        ctx->launches += 3;
+        if ((rc = fm_fill_image(ctx, d_bwt, N, primary, lut, nplanes, h.nblocks, d_planes, d_sa, rate, d_mark,
+                                d_samples)) != TC_OK)
+            break;
         fm->hdr = h;
         cudaError_t e = cudaMemcpyAsync(blob, &fm->hdr, sizeof(FmHeader), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -130,8 +130,10 @@ int tc_radix_sort_pairs(tc_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, u
     uint64_t *ki = k0, *ko = k1;
     uint32_t *vi = v0, *vo = v1;
     for (int p = 0; p < npass; p++) {
+        ctx->prof_bytes_next = 8 * n; // keys read
         TC_LAUNCH(ctx, rs_hist_kernel, (unsigned)tiles, RS_T, 0, ki, n, shifts[p], hist, tiles);
         TC_TRY(tc_scan_exclusive_u32(ctx, hist, hist, 256 * tiles, (uint32_t *)nullptr));
+        ctx->prof_bytes_next = 24 * n; // (8 B key + 4 B value) read and written
         TC_LAUNCH(ctx, rs_scatter_kernel, (unsigned)tiles, RS_T, sizeof(RsSmem), ki, vi, ko, vo, n, shifts[p], hist,
                   tiles);
         std::swap(ki, ko);
