@@ -238,7 +238,7 @@ def run_b200(args):
     def pass_ms(prefixes):
         return sum(v[1] for k, v in prof.items() if k.split("<")[0].strip().startswith(prefixes)) / PSTEPS
 
-    mtf_ms = pass_ms(("mtf_",))
+    mtf_ms = pass_ms(("mtf",))
     rle_ms = pass_ms(("rle_",))
     bwt_ms = tot_ms / PSTEPS - mtf_ms - rle_ms
     mtf_bytes = N * 3                     # u8 symbol in, u16 index out (sigma = 257)

@@ -109,200 +109,282 @@ struct TState {
     }
 };
 
-// ---- K1: recency list of each chunk -------------------------------------------------
+// ---- encode v2: warp per chunk ------------------------------------------------------------
+constexpr int VSMAX = 288;           // virtual slots: sigma rounded up to a multiple of 32
+constexpr int ENC_WARPS = 8;         // warps (chunks) per CTA
+constexpr int WIN_WORDS = 64;        // recency window of the prologue: 2048 positions
+
+// K1: last occurrence (global position + 1, 0 = absent) of every rank inside each chunk
 template <class Src>
-__global__ void mtf_recency_kernel(Src src, Lut lut, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t sigma,
-                                   uint16_t *__restrict__ rec, uint32_t *__restrict__ reclen) {
-    extern __shared__ uint32_t smem[];
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+    mtf2_lastocc_kernel(Src src, Lut lut, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t VS,
+                        uint32_t *__restrict__ lastocc) {
     __shared__ uint16_t s_rank[SIGMAX];
+    __shared__ uint32_t lo[ENC_WARPS][VSMAX];
     for (int j = threadIdx.x; j < SIGMAX; j += blockDim.x) s_rank[j] = lut.rank[j];
-    __syncthreads();
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nchunks) return;
-    TState seen{smem}; // 9 words per thread
-#pragma unroll
-    for (int w = 0; w < 9; w++) seen.word(w) = 0;
-    uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
-    uint16_t *out = rec + k * sigma;
-    uint32_t n = 0;
-    // walk backwards in 16-symbol vectors
-    uint64_t i = end;
-    while (i > beg) {
-        uint64_t vb = (i - 1) & ~uint64_t(15);
-        if (vb < beg) vb = beg;
-        int c[16];
-        int cnt = (int)(i - vb);
-        if (cnt == 16 && src.can_vec(vb)) {
-            src.load_vec(vb, c);
-        } else {
-            for (int q = 0; q < cnt; q++) c[q] = src.at(vb + q);
-        }
-        for (int q = cnt - 1; q >= 0; q--) {
-            int r = s_rank[c[q]];
-            uint32_t w = seen.word(r >> 5);
-            uint32_t bit = 1u << (r & 31);
-            if (!(w & bit)) {
-                seen.word(r >> 5) = w | bit;
-                out[n++] = (uint16_t)r;
-            }
-        }
-        i = vb;
-        if (n == sigma) break;
-    }
-    reclen[k] = n;
-}
-
-// dst = r ++ (acc \ r) -- the list after applying a chunk with recency list r to list acc.
-__device__ __forceinline__ int compose_lists(uint16_t *dst, const uint16_t *acc, int alen, const uint16_t *r, int rlen,
-                                             uint32_t *bm) {
-    const unsigned lane = lane_id();
-    if (lane < 9) bm[lane] = 0;
-    __syncwarp();
-    for (int j = lane; j < rlen; j += 32) {
-        uint32_t c = r[j];
-        dst[j] = (uint16_t)c;
-        atomicOr(&bm[c >> 5], 1u << (c & 31));
-    }
-    __syncwarp();
-    int out = rlen;
-    for (int b = 0; b < alen; b += 32) {
-        int j = b + lane;
-        bool valid = j < alen;
-        uint32_t c = valid ? acc[j] : 0;
-        bool keep = valid && !((bm[c >> 5] >> (c & 31)) & 1);
-        unsigned m = __ballot_sync(TC_FULL, keep);
-        if (keep) dst[out + __popc(m & lanemask_lt())] = (uint16_t)c;
-        out += __popc(m);
-    }
-    __syncwarp();
-    return out;
-}
-
-// ---- K2a: exclusive chain inside each tile of G chunks (one warp per tile) ---------------
-__global__ void __launch_bounds__(128)
-    mtf_tile_chain_kernel(const uint16_t *__restrict__ rec, const uint32_t *__restrict__ reclen, uint64_t nchunks,
-                          uint32_t G, uint32_t sigma, uint16_t *__restrict__ part, uint32_t *__restrict__ partlen,
-                          uint16_t *__restrict__ tilesum, uint32_t *__restrict__ tilesumlen, uint64_t ntiles) {
-    __shared__ uint16_t bufs[4][2][LISTPAD];
-    __shared__ uint32_t bms[4][9];
     const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
-    uint64_t t = (uint64_t)blockIdx.x * 4 + w;
-    if (t >= ntiles) return;
-    uint16_t *A = bufs[w][0], *B = bufs[w][1];
-    int alen = 0;
-    uint64_t k0 = t * G, k1 = k0 + G < nchunks ? k0 + G : nchunks;
-    for (uint64_t k = k0; k < k1; k++) {
-        for (int j = lane; j < alen; j += 32) part[k * sigma + j] = A[j];
-        if (lane == 0) partlen[k] = alen;
-        alen = compose_lists(B, A, alen, rec + k * sigma, (int)reclen[k], bms[w]);
-        uint16_t *tmp = A;
-        A = B;
-        B = tmp;
+    for (int j = lane; j < VSMAX; j += 32) lo[w][j] = 0;
+    __syncthreads();
+    uint64_t k = (uint64_t)blockIdx.x * ENC_WARPS + w;
+    if (k >= nchunks) return;
+    uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+    for (uint64_t b0 = beg; b0 < end; b0 += 8 * 32) {
+        int c[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint64_t pos = b0 + q * 32 + lane;
+            c[q] = pos < end ? (int)s_rank[src.at(pos)] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint64_t pos = b0 + q * 32 + lane;
+            bool valid = c[q] >= 0;
+            unsigned peers = match_bits<9>((uint32_t)c[q], valid);
+            bool is_last = valid && (peers & ~((2u << lane) - 1)) == 0; // no later lane holds the same rank
+            if (is_last) lo[w][c[q]] = (uint32_t)pos + 1;
+            __syncwarp();
+        }
     }
-    for (int j = lane; j < alen; j += 32) tilesum[t * sigma + j] = A[j];
-    if (lane == 0) tilesumlen[t] = alen;
+    for (int j = lane; j < (int)VS; j += 32) lastocc[k * VS + j] = lo[w][j];
 }
 
-// ---- K2b: exclusive chain over tiles from L0 = identity (one warp) ------------------------
-__global__ void __launch_bounds__(32)
-    mtf_top_chain_kernel(const uint16_t *__restrict__ tilesum, const uint32_t *__restrict__ tilesumlen,
-                         uint64_t ntiles, uint32_t sigma, uint16_t *__restrict__ tileprefix,
-                         uint16_t *__restrict__ final_list) {
-    __shared__ uint16_t bufs[2][LISTPAD];
-    __shared__ uint32_t bm[9];
+// K2a: exclusive running max over the chunks of each tile (in place) + tile totals
+__global__ void mtf2_scan_tiles_kernel(uint32_t *__restrict__ lastocc, uint64_t nchunks, uint32_t G, uint32_t VS,
+                                       uint32_t *__restrict__ tiletot) {
+    uint32_t c = threadIdx.x;
+    if (c >= VS) return;
+    uint64_t k0 = (uint64_t)blockIdx.x * G, k1 = k0 + G < nchunks ? k0 + G : nchunks;
+    uint32_t run = 0;
+    for (uint64_t kb = k0; kb < k1; kb += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = (kb + q < k1) ? lastocc[(kb + q) * VS + c] : 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (kb + q < k1) lastocc[(kb + q) * VS + c] = run;
+            run = max(run, v[q]);
+        }
+    }
+    tiletot[(uint64_t)blockIdx.x * VS + c] = run;
+}
+// K2b: exclusive running max over tiles (in place); finalocc = last occurrence in the whole input
+__global__ void mtf2_scan_top_kernel(uint32_t *__restrict__ tiletot, uint64_t ntiles, uint32_t VS,
+                                     uint32_t *__restrict__ finalocc) {
+    uint32_t c = threadIdx.x;
+    if (c >= VS) return;
+    uint32_t run = 0;
+    for (uint64_t tb = 0; tb < ntiles; tb += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = (tb + q < ntiles) ? tiletot[(tb + q) * VS + c] : 0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            if (tb + q < ntiles) tiletot[(tb + q) * VS + c] = run;
+            run = max(run, v[q]);
+        }
+    }
+    finalocc[c] = run;
+}
+
+// List position of every rank at text position `start`, from its last occurrence before `start`
+// (T[c] = position + 1, 0 = never seen: those keep the alphabet order behind all seen ones).
+// pos(c) = number of ranks with a more recent occurrence.  Recent occurrences (within 2048
+// positions) are ranked with a bitmap + prefix popcounts; the few older ones pairwise.
+// tvals: 9 values per lane, rank j = lane + 32*i.  Writes pos into posv[9].  Warp-collective.
+struct WarpPro {
+    uint32_t win[WIN_WORDS];
+    uint32_t pre[WIN_WORDS];
+    uint32_t okey[VSMAX];
+    uint32_t ocount;
+};
+__device__ __forceinline__ void list_positions(const uint32_t *tvals, uint64_t start, uint32_t sigma, WarpPro &P,
+                                               uint32_t *posv) {
     const unsigned lane = lane_id();
-    uint16_t *A = bufs[0], *B = bufs[1];
-    for (int j = lane; j < (int)sigma; j += 32) A[j] = (uint16_t)j;
+    P.win[lane] = 0;
+    P.win[lane + 32] = 0;
+    if (lane == 0) P.ocount = 0;
     __syncwarp();
-    for (uint64_t t = 0; t < ntiles; t++) {
-        for (int j = lane; j < (int)sigma; j += 32) tileprefix[t * sigma + j] = A[j];
-        compose_lists(B, A, (int)sigma, tilesum + t * sigma, (int)tilesumlen[t], bm);
-        uint16_t *tmp = A;
-        A = B;
-        B = tmp;
+    uint32_t key[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        uint32_t c = lane + 32 * i;
+        uint32_t T = tvals[i];
+        // distance back to the last occurrence (>= 1); never-seen ranks sort after every seen one
+        key[i] = T ? (uint32_t)(start - (T - 1)) : (0x80000000u + c);
+        if (c < sigma && key[i] <= WIN_WORDS * 32) atomicOr(&P.win[(key[i] - 1) >> 5], 1u << ((key[i] - 1) & 31));
     }
-    for (int j = lane; j < (int)sigma; j += 32) final_list[j] = A[j];
+    __syncwarp();
+    // prefix popcounts of the window, two words per lane
+    uint32_t p0 = __popc(P.win[2 * lane]), p1 = __popc(P.win[2 * lane + 1]);
+    uint32_t inc = warp_incl_sum(p0 + p1);
+    P.pre[2 * lane] = inc - p0 - p1;
+    P.pre[2 * lane + 1] = inc - p1;
+    uint32_t m_in = __shfl_sync(TC_FULL, inc, 31);
+    // collect the keys outside the window
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        uint32_t c = lane + 32 * i;
+        bool out = c < sigma && key[i] > WIN_WORDS * 32;
+        unsigned m = __ballot_sync(TC_FULL, out);
+        uint32_t base = P.ocount;
+        __syncwarp();
+        if (out) P.okey[base + __popc(m & lanemask_lt())] = key[i];
+        if (lane == 0) P.ocount = base + __popc(m);
+        __syncwarp();
+    }
+    uint32_t m_out = P.ocount;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        uint32_t c = lane + 32 * i;
+        uint32_t p = 0;
+        if (c < sigma) {
+            if (key[i] <= WIN_WORDS * 32) {
+                uint32_t b = key[i] - 1;
+                p = P.pre[b >> 5] + __popc(P.win[b >> 5] & ((1u << (b & 31)) - 1));
+            } else {
+                p = m_in;
+                for (uint32_t e = 0; e < m_out; e++) p += P.okey[e] < key[i];
+            }
+        }
+        posv[i] = p;
+    }
+    __syncwarp();
 }
 
-// ---- K3: replay ----------------------------------------------------------------------------
-// per-thread shared state: LASTW words of last[] (u16 slot per rank) + BW bitmap words.
+// K3: replay, one warp per chunk, 32 positions per step (lane t <-> position base + t).
+// Slots: list position j at chunk start owns virtual slot VS-1-j; chunk offset o owns slot VS+o.
+// bits[] marks slots that are the latest occurrence of their rank (always exactly sigma bits),
+// pre[] holds the exclusive prefix popcount per word, last[r] the slot of rank r.
+struct WarpRep {
+    uint32_t bits[(VSMAX + 1024) / 32];
+    uint32_t pre[(VSMAX + 1024) / 32];
+    uint16_t last[VSMAX];
+};
 template <class Src>
-__global__ void mtf_replay_kernel(Src src, Lut lut, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t G,
-                                  uint32_t sigma, const uint16_t *__restrict__ part,
-                                  const uint32_t *__restrict__ partlen, const uint16_t *__restrict__ tileprefix,
-                                  uint16_t *__restrict__ idx_out) {
-    extern __shared__ uint32_t smem[];
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+    mtf2_replay_kernel(Src src, Lut lut, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t G, uint32_t sigma,
+                       uint32_t VS, const uint32_t *__restrict__ lastocc, const uint32_t *__restrict__ tiletot,
+                       uint16_t *__restrict__ idx_out) {
     __shared__ uint16_t s_rank[SIGMAX];
+    __shared__ WarpPro pro[ENC_WARPS];
+    __shared__ WarpRep rep[ENC_WARPS];
     for (int j = threadIdx.x; j < SIGMAX; j += blockDim.x) s_rank[j] = lut.rank[j];
     __syncthreads();
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    uint64_t k = (uint64_t)blockIdx.x * ENC_WARPS + w;
     if (k >= nchunks) return;
-    TState last{smem};
-    TState bits{smem + LASTW * blockDim.x};
-    const int BW = (int)((sigma + L + 31) / 32);
-    for (int w = 0; w < BW; w++) bits.word(w) = 0;
-    for (int w = 0; w < (int)sigma / 32; w++) bits.word(w) = 0xffffffffu;
-    if (sigma & 31) bits.word(sigma / 32) = (1u << (sigma & 31)) - 1;
-    for (int r = 0; r < (int)sigma; r++) last.set16(r, 0xffff);
-    // incoming order: the tile-local partial list first, then the tile prefix for the rest.
-    // list position j owns virtual slot sigma-1-j (front of the list == most recent).
-    uint32_t pl = partlen[k];
-    const uint16_t *pp = part + k * sigma;
-    for (uint32_t j = 0; j < pl; j++) last.set16(pp[j], (uint16_t)(sigma - 1 - j));
-    const uint16_t *tp = tileprefix + (k / G) * sigma;
-    uint32_t j2 = pl;
-    for (uint32_t j = 0; j < sigma && j2 < sigma; j++) {
-        uint16_t r = tp[j];
-        if (last.get16(r) == 0xffff) last.set16(r, (uint16_t)(sigma - 1 - j2++));
-    }
-    uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
-    const bool vec_out = (reinterpret_cast<uintptr_t>(idx_out + beg) & 15) == 0;
-    for (uint64_t vb = beg; vb < end; vb += 16) {
-        int c[16];
-        int cnt = (int)(end - vb < 16 ? end - vb : 16);
-        if (cnt == 16 && src.can_vec(vb)) {
-            src.load_vec(vb, c);
-        } else {
-            for (int q = 0; q < cnt; q++) c[q] = src.at(vb + q);
+    WarpRep &R = rep[w];
+    const uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+    const int NW = (int)((VS + L) / 32);
+    // ---- prologue: incoming list order -> slots
+    {
+        uint32_t tv[9], pv[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            uint32_t c = lane + 32 * i;
+            tv[i] = c < VS ? max(lastocc[k * VS + c], tiletot[(k / G) * VS + c]) : 0;
         }
-        uint32_t o[16];
-        for (int q = 0; q < cnt; q++) {
-            const int r = s_rank[c[q]];
-            const uint32_t a = last.get16(r);
-            const uint32_t now = sigma + (uint32_t)(vb - beg) + q;
-            const int wa = a >> 5, wn = now >> 5;
-            // popcount of set bits strictly between a and now (bit `now` is not set yet)
-            uint32_t cntbits;
-            uint32_t wa_bits = bits.word(wa);
-            uint32_t hi_a = (wa_bits >> (a & 31)) >> 1; // bits above a inside its word
-            if (wa == wn) {
-                cntbits = __popc(hi_a & ((1u << ((now & 31) - (a & 31) - 1)) - 1));
-            } else {
-                cntbits = __popc(hi_a);
-                for (int w = wa + 1; w < wn; w++) cntbits += __popc(bits.word(w));
-                cntbits += __popc(bits.word(wn) & ((1u << (now & 31)) - 1));
+        list_positions(tv, beg, sigma, pro[w], pv);
+        for (int j = lane; j < NW; j += 32) R.bits[j] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            uint32_t c = lane + 32 * i;
+            if (c < sigma) {
+                uint32_t slot = VS - 1 - pv[i];
+                R.last[c] = (uint16_t)slot;
+                atomicOr(&R.bits[slot >> 5], 1u << (slot & 31));
             }
-            o[q] = cntbits;
-            bits.word(wa) = wa_bits & ~(1u << (a & 31));
-            bits.word(wn) |= 1u << (now & 31);
-            last.set16(r, (uint16_t)now);
         }
-        if (cnt == 16 && vec_out) {
-            uint4 w0, w1;
-            w0.x = o[0] | (o[1] << 16);
-            w0.y = o[2] | (o[3] << 16);
-            w0.z = o[4] | (o[5] << 16);
-            w0.w = o[6] | (o[7] << 16);
-            w1.x = o[8] | (o[9] << 16);
-            w1.y = o[10] | (o[11] << 16);
-            w1.z = o[12] | (o[13] << 16);
-            w1.w = o[14] | (o[15] << 16);
-            *reinterpret_cast<uint4 *>(idx_out + vb) = w0;
-            *reinterpret_cast<uint4 *>(idx_out + vb + 8) = w1;
-        } else {
-            for (int q = 0; q < cnt; q++) idx_out[vb + q] = (uint16_t)o[q];
+        __syncwarp();
+    }
+    const unsigned lt = lanemask_lt();
+    for (uint32_t o = 0; beg + o < end; o += 32) {
+        // prefix popcounts of the bitmap as of the start of this step
+        {
+            uint32_t a0 = 2 * lane < (unsigned)NW ? R.bits[2 * lane] : 0;
+            uint32_t a1 = 2 * lane + 1 < (unsigned)NW ? R.bits[2 * lane + 1] : 0;
+            uint32_t q0 = __popc(a0), q1 = __popc(a1);
+            uint32_t inc = warp_incl_sum(q0 + q1);
+            if (2 * lane < (unsigned)NW) R.pre[2 * lane] = inc - q0 - q1;
+            if (2 * lane + 1 < (unsigned)NW) R.pre[2 * lane + 1] = inc - q1;
         }
+        __syncwarp();
+        const uint64_t pos = beg + o + lane;
+        const bool valid = pos < end;
+        const uint32_t c = valid ? (uint32_t)s_rank[src.at(pos)] : 0;
+        const uint32_t base = VS + o;
+        const unsigned peers = match_bits<9>(c, valid);
+        const unsigned lower = peers & lt;
+        const bool has_prev = valid && lower != 0;
+        const bool first = valid && lower == 0;
+        const bool is_last = valid && (peers & ~((2u << lane) - 1)) == 0;
+        const int u = has_prev ? 31 - __clz(lower) : -1; // previous lane with the same rank
+        uint32_t rank = 0;
+        uint32_t a = 0;
+        uint32_t r0 = 0;
+        if (first) {
+            a = R.last[c];
+            uint32_t wa = a >> 5;
+            uint32_t below = R.pre[wa] + __popc(R.bits[wa] & ((2u << (a & 31)) - 1)); // set bits at slots <= a
+            r0 = sigma - below;                                                       // list position at step start
+        }
+        // ranks first touched in this step: r0 minus the earlier-touched ranks that were ahead, plus
+        // the number of distinct ranks touched earlier in the step
+        const unsigned firstmask = __ballot_sync(TC_FULL, first);
+        {
+            unsigned ltm = 0, eq = firstmask;
+#pragma unroll
+            for (int bit = 8; bit >= 0; bit--) {
+                bool mb = (r0 >> bit) & 1;
+                unsigned Bm = __ballot_sync(TC_FULL, first && mb);
+                if (mb) {
+                    ltm |= eq & ~Bm;
+                    eq &= Bm;
+                } else {
+                    eq &= ~Bm;
+                }
+            }
+            if (first) rank = r0 - __popc(ltm & lt & firstmask) + __popc(firstmask & lt);
+        }
+        // ranks seen earlier in this step: distinct ranks strictly between the two occurrences
+        unsigned pend = __ballot_sync(TC_FULL, has_prev);
+        while (pend) {
+            int l = __ffs(pend) - 1;
+            int us = __shfl_sync(TC_FULL, u, l);
+            unsigned Bq = __ballot_sync(TC_FULL, valid && u < us); // lanes whose previous occurrence is before us
+            if ((int)lane == l) rank = __popc(Bq & lt & ~((2u << us) - 1));
+            pend &= pend - 1;
+        }
+        if (valid) idx_out[pos] = (uint16_t)rank;
+        // state update
+        if (first) atomicAnd(&R.bits[a >> 5], ~(1u << (a & 31)));
+        unsigned lastmask = __ballot_sync(TC_FULL, is_last);
+        if (lane == 0) R.bits[base >> 5] = lastmask;
+        if (is_last) R.last[c] = (uint16_t)(base + lane);
+        __syncwarp();
+    }
+}
+
+// final list = order at the end of the input (seqToMTF's second component)
+__global__ void __launch_bounds__(32)
+    mtf2_final_kernel(const uint32_t *__restrict__ finalocc, uint64_t N, uint32_t sigma, uint32_t VS,
+                      uint16_t *__restrict__ final_list) {
+    __shared__ WarpPro pro;
+    const unsigned lane = lane_id();
+    uint32_t tv[9], pv[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        uint32_t c = lane + 32 * i;
+        tv[i] = c < VS ? finalocc[c] : 0;
+    }
+    list_positions(tv, N, sigma, pro, pv);
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        uint32_t c = lane + 32 * i;
+        if (c < sigma) final_list[pv[i]] = (uint16_t)c;
     }
 }
 
@@ -414,7 +496,7 @@ template <class Src>
 int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *final_list, uint32_t *sigma_out) {
     *sigma_out = 0;
     if (N == 0) return TC_OK;
-    if (N >= 0xfffffffeull) return TC_E_TOOBIG;
+    if (N >= 0x7fffffffull) return TC_E_TOOBIG; // recency keys are 32-bit distances (see list_positions)
     WsMark mk = tc_ws_mark(ctx);
     // alphabet = nubSeq' (sorted, Nothing first)
     uint32_t *d_present;
@@ -436,33 +518,27 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
             lut.rank[c] = 0;
         }
     }
-    const uint32_t L = pick_chunk_len(ctx, N, 64, 1024);
+    const uint32_t VS = (sigma + 31) / 32 * 32;
+    // chunk length: a multiple of 32, enough chunks to fill the machine with warps
+    uint64_t Lw = ceil_div_u64(N, (uint64_t)ctx->sm_count * 64);
+    Lw = (Lw + 31) / 32 * 32;
+    const uint32_t L = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(Lw, 256), 1024);
     const uint64_t nchunks = ceil_div_u64(N, L);
-    const uint32_t G = 128;
+    const uint32_t G = 64;
     const uint64_t ntiles = ceil_div_u64(nchunks, G);
-    uint16_t *rec, *part, *tilesum, *tileprefix, *d_final;
-    uint32_t *reclen, *partlen, *tilesumlen;
-    TC_TRY(ws_alloc(ctx, nchunks * sigma, &rec));
-    TC_TRY(ws_alloc(ctx, nchunks, &reclen));
-    TC_TRY(ws_alloc(ctx, nchunks * sigma, &part));
-    TC_TRY(ws_alloc(ctx, nchunks, &partlen));
-    TC_TRY(ws_alloc(ctx, ntiles * sigma, &tilesum));
-    TC_TRY(ws_alloc(ctx, ntiles, &tilesumlen));
-    TC_TRY(ws_alloc(ctx, ntiles * sigma, &tileprefix));
+    uint32_t *lastocc, *tiletot, *finalocc;
+    uint16_t *d_final;
+    TC_TRY(ws_alloc(ctx, nchunks * VS, &lastocc));
+    TC_TRY(ws_alloc(ctx, ntiles * VS, &tiletot));
+    TC_TRY(ws_alloc(ctx, VSMAX, &finalocc));
     TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
-    const int T = 64;
-    unsigned cgrid = (unsigned)ceil_div_u64(nchunks, T);
-    TC_LAUNCH(ctx, (mtf_recency_kernel<Src>), cgrid, T, 9 * T * sizeof(uint32_t), src, lut, N, L, nchunks, sigma, rec,
-              reclen);
-    TC_LAUNCH(ctx, mtf_tile_chain_kernel, (unsigned)ceil_div_u64(ntiles, 4), 128, 0, rec, reclen, nchunks, G, sigma,
-              part, partlen, tilesum, tilesumlen, ntiles);
-    TC_LAUNCH(ctx, mtf_top_chain_kernel, 1, 32, 0, tilesum, tilesumlen, ntiles, sigma, tileprefix, d_final);
-    const int BW = (int)((sigma + L + 31) / 32);
-    size_t smem = (size_t)(LASTW + BW) * T * sizeof(uint32_t);
-    if (smem > 48 * 1024)
-        TC_CUDA(cudaFuncSetAttribute(mtf_replay_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TC_LAUNCH(ctx, (mtf_replay_kernel<Src>), cgrid, T, smem, src, lut, N, L, nchunks, G, sigma, part, partlen,
-              tileprefix, d_idx);
+    unsigned cgrid = (unsigned)ceil_div_u64(nchunks, ENC_WARPS);
+    TC_LAUNCH(ctx, (mtf2_lastocc_kernel<Src>), cgrid, ENC_WARPS * 32, 0, src, lut, N, L, nchunks, VS, lastocc);
+    TC_LAUNCH(ctx, mtf2_scan_tiles_kernel, (unsigned)ntiles, VSMAX, 0, lastocc, nchunks, G, VS, tiletot);
+    TC_LAUNCH(ctx, mtf2_scan_top_kernel, 1, VSMAX, 0, tiletot, ntiles, VS, finalocc);
+    TC_LAUNCH(ctx, (mtf2_replay_kernel<Src>), cgrid, ENC_WARPS * 32, 0, src, lut, N, L, nchunks, G, sigma, VS, lastocc,
+              tiletot, d_idx);
+    TC_LAUNCH(ctx, mtf2_final_kernel, 1, 32, 0, finalocc, N, sigma, VS, d_final);
     uint16_t *h_final = (uint16_t *)ctx->h_scal;
     TC_CUDA(cudaMemcpyAsync(h_final, d_final, sigma * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
