@@ -1,0 +1,308 @@
+{-# LANGUAGE ForeignFunctionInterface #-}
+{-# LANGUAGE MultiWayIf               #-}
+
+-- |
+-- Module      : Data.TextCompression.B200
+-- Description : `foreign import ccall` shim over libtc_b200.so (include/tc_b200.h)
+--
+-- The thin host layer the text-compression package binds to reach the B200 kernels.
+-- Every function here replaces one function of the reference's "Internal" modules and keeps
+-- its type, so the public modules (Data.BWT, Data.MTF, Data.RLE, Data.FMIndex) and their
+-- export lists stay as they are (see INTEGRATION.md for the per-function patch).
+--
+-- NOTE: written without a Haskell toolchain (no GHC in the build image or on the GPU box);
+-- it targets base ^>=4.12 / containers 0.6 like the reference, but has not been compiled.
+-- All semantics live below the C ABI, where they are tested bit-for-bit against the CPU
+-- restatement of the reference (tests/test_gpu_parity.py).
+--
+-- Marshalling: `Seq (Maybe b)` over byte-derived symbols <-> int16 (-1 == Nothing);
+-- `Seq Int` <-> uint16 / int64; buffers are pinned (tc_host_alloc) so the H2D/D2H copies inside
+-- the library run at full PCIe rate.  Error codes map back to the exceptions the reference
+-- throws: TC_E_FROMJUST -> `fromJust Nothing`, TC_E_INDEX -> `index out of bounds`.
+module Data.TextCompression.B200
+  ( -- * context
+    withB200
+    -- * Data.BWT.Internal replacements
+  , createSuffixArrayW8
+  , toBWTW8
+  , fromBWTW8
+    -- * Data.MTF.Internal replacements
+  , seqToMTFW8
+  , seqFromMTFW8
+    -- * Data.RLE.Internal replacements
+  , seqToRLEW8
+  , seqFromRLEW8
+    -- * composed helpers (device-resident BWT -> MTF -> RLE)
+  , bwtMtfRleW8
+    -- * Data.FMIndex.Internal replacements
+  , B200FM
+  , buildFMIndexW8
+  , countFMIndexW8
+  , locateFMIndexW8
+  ) where
+
+import           Control.Exception     (ErrorCall (..), bracket, throwIO)
+import           Control.Monad         (forM, forM_, when)
+import qualified Data.ByteString       as BS
+import qualified Data.ByteString.Unsafe as BSU
+import           Data.Foldable         (toList)
+import           Data.Int              (Int16, Int64)
+import           Data.Sequence         (Seq)
+import qualified Data.Sequence         as DS
+import           Data.Word             (Word16, Word32, Word64, Word8)
+import           Foreign.C.String      (CString, peekCString)
+import           Foreign.C.Types       (CInt (..), CSize (..))
+import           Foreign.ForeignPtr    (ForeignPtr, newForeignPtr, withForeignPtr)
+import           Foreign.Marshal.Alloc (alloca)
+import           Foreign.Marshal.Array (peekArray, pokeArray)
+import           Foreign.Ptr           (FunPtr, Ptr, castPtr, nullPtr)
+import           Foreign.Storable      (peek, peekByteOff)
+import           System.IO.Unsafe      (unsafePerformIO)
+
+data TcCtx
+data TcFm
+
+-- include/tc_b200.h ------------------------------------------------------------------
+foreign import ccall safe "tc_ctx_create"   c_ctx_create  :: CInt -> Ptr (Ptr TcCtx) -> IO CInt
+foreign import ccall safe "tc_ctx_destroy"  c_ctx_destroy :: Ptr TcCtx -> IO ()
+foreign import ccall safe "tc_strerror"     c_strerror    :: CInt -> IO CString
+foreign import ccall safe "tc_last_error"   c_last_error  :: Ptr TcCtx -> IO CString
+foreign import ccall safe "tc_host_alloc"   c_host_alloc  :: CSize -> IO (Ptr a)
+foreign import ccall safe "&tc_host_free"   p_host_free   :: FunPtr (Ptr a -> IO ())
+foreign import ccall safe "tc_bwt_encode"
+  c_bwt_encode :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Ptr Word8 -> Ptr Word64 -> Ptr Word32 -> IO CInt
+foreign import ccall safe "tc_bwt_decode"
+  c_bwt_decode :: Ptr TcCtx -> Ptr Int16 -> Word64 -> Ptr Word8 -> Word64 -> Ptr Word64 -> IO CInt
+foreign import ccall safe "tc_mtf_encode"
+  c_mtf_encode :: Ptr TcCtx -> Ptr Int16 -> Word64 -> Ptr Word16 -> Ptr Int16 -> Ptr Word32 -> IO CInt
+foreign import ccall safe "tc_mtf_decode"
+  c_mtf_decode :: Ptr TcCtx -> Ptr Word16 -> Word64 -> Ptr Int16 -> Word32 -> Ptr Int16 -> IO CInt
+foreign import ccall safe "tc_rle_encode"
+  c_rle_encode :: Ptr TcCtx -> Ptr Int16 -> Word64 -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr Word64 -> IO CInt
+foreign import ccall safe "tc_rle_decode"
+  c_rle_decode :: Ptr TcCtx -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr Int16 -> Word64 -> Ptr Word64 -> IO CInt
+foreign import ccall safe "tc_bwt_mtf_rle_encode"
+  c_bwt_mtf_rle :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr () -> IO CInt
+foreign import ccall safe "tc_fm_build"
+  c_fm_build :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Word32 -> Ptr (Ptr TcFm) -> IO CInt
+foreign import ccall safe "&tc_fm_free" p_fm_free :: FunPtr (Ptr TcFm -> IO ())
+foreign import ccall safe "tc_fm_count"
+  c_fm_count :: Ptr TcCtx -> Ptr TcFm -> Ptr Word8 -> Ptr Word64 -> Word64 -> Ptr Int64 -> IO CInt
+foreign import ccall safe "tc_fm_locate"
+  c_fm_locate :: Ptr TcCtx -> Ptr TcFm -> Ptr Word8 -> Ptr Word64 -> Word64 -> Ptr Word64 -> Ptr Word64
+              -> Word64 -> Ptr Word64 -> IO CInt
+
+tcECap, tcEFromJust, tcEIndex :: CInt
+tcECap      = -2
+tcEFromJust = -3
+tcEIndex    = -4
+
+-- | One context per call keeps the functions pure and re-entrant, like the reference's
+-- (`tc_ctx` must not be shared between OS threads).  A long-running caller can hoist this.
+withB200 :: (Ptr TcCtx -> IO a) -> IO a
+withB200 = bracket create c_ctx_destroy
+  where
+    create = alloca $ \pp -> do
+      rc <- c_ctx_create 0 pp
+      when (rc /= 0) $ c_strerror rc >>= peekCString >>= throwIO . ErrorCall
+      peek pp
+
+check :: Ptr TcCtx -> CInt -> IO ()
+check ctx rc
+  | rc == 0           = pure ()
+  | rc == tcEFromJust = throwIO (ErrorCall "Maybe.fromJust: Nothing")
+  | rc == tcEIndex    = throwIO (ErrorCall "index out of bounds")
+  | otherwise         = do
+      s <- c_strerror rc >>= peekCString
+      d <- c_last_error ctx >>= peekCString
+      throwIO (ErrorCall ("libtc_b200: " ++ s ++ " " ++ d))
+
+pinned :: Int -> IO (ForeignPtr a)
+pinned bytes = c_host_alloc (fromIntegral (max 1 bytes)) >>= newForeignPtr p_host_free
+
+maybeToI16 :: Maybe Word8 -> Int16
+maybeToI16 Nothing  = -1
+maybeToI16 (Just w) = fromIntegral w
+
+i16ToMaybe :: Int16 -> Maybe Word8
+i16ToMaybe x | x < 0     = Nothing
+             | otherwise = Just (fromIntegral x)
+
+-- | createSuffixArray (Data/BWT/Internal.hs:110-134) for Word8 text: suffixstartpos per rank.
+createSuffixArrayW8 :: BS.ByteString -> Seq Int
+createSuffixArrayW8 xs
+  | BS.null xs = DS.singleton 1
+  | otherwise  = unsafePerformIO $ withB200 $ \ctx ->
+      BSU.unsafeUseAsCStringLen xs $ \(p, n) -> do
+        bwt <- pinned (n + 1)
+        sa  <- pinned (4 * (n + 1))
+        alloca $ \pprim -> withForeignPtr bwt $ \pb -> withForeignPtr sa $ \ps -> do
+          c_bwt_encode ctx (castPtr p) (fromIntegral n) pb pprim ps >>= check ctx
+          DS.fromList . map fromIntegral <$> (peekArray (n + 1) ps :: IO [Word32])
+
+-- | toBWT (Data/BWT.hs:55-64) on a ByteString: the BWT as `Seq (Maybe Word8)`.
+toBWTW8 :: BS.ByteString -> Seq (Maybe Word8)
+toBWTW8 xs
+  | BS.null xs = DS.empty
+  | otherwise  = unsafePerformIO $ withB200 $ \ctx ->
+      BSU.unsafeUseAsCStringLen xs $ \(p, n) -> do
+        bwt <- pinned (n + 1)
+        alloca $ \pprim -> withForeignPtr bwt $ \pb -> do
+          c_bwt_encode ctx (castPtr p) (fromIntegral n) pb pprim nullPtr >>= check ctx
+          prim <- fromIntegral <$> peek pprim
+          ws   <- peekArray (n + 1) pb
+          pure $ DS.fromList [ if i == prim then Nothing else Just w | (i, w) <- zip [0 :: Int ..] ws ]
+
+-- | fromBWT (Data/BWT.hs:93-104) on `Seq (Maybe Word8)`.
+fromBWTW8 :: Seq (Maybe Word8) -> BS.ByteString
+fromBWTW8 s
+  | DS.null s = BS.empty
+  | otherwise = unsafePerformIO $ withB200 $ \ctx -> do
+      let n = DS.length s
+      inp <- pinned (2 * n)
+      out <- pinned n
+      alloca $ \pn -> withForeignPtr inp $ \pi' -> withForeignPtr out $ \po -> do
+        pokeArray pi' (map maybeToI16 (toList s))
+        c_bwt_decode ctx pi' (fromIntegral n) po (fromIntegral n) pn >>= check ctx
+        m <- fromIntegral <$> peek pn
+        BS.packCStringLen (castPtr po, m)
+
+-- | seqToMTF (Data/MTF/Internal.hs:128-175): (indices, FINAL list).
+seqToMTFW8 :: Seq (Maybe Word8) -> (Seq Int, Seq (Maybe Word8))
+seqToMTFW8 s
+  | DS.null s = (DS.empty, DS.empty)
+  | otherwise = unsafePerformIO $ withB200 $ \ctx -> do
+      let n = DS.length s
+      inp <- pinned (2 * n)
+      idx <- pinned (2 * n)
+      fin <- pinned (2 * 257)
+      alloca $ \psig -> withForeignPtr inp $ \pi' -> withForeignPtr idx $ \px -> withForeignPtr fin $ \pf -> do
+        pokeArray pi' (map maybeToI16 (toList s))
+        c_mtf_encode ctx pi' (fromIntegral n) px pf psig >>= check ctx
+        sg <- fromIntegral <$> peek psig
+        is <- peekArray n px :: IO [Word16]
+        fs <- peekArray sg pf
+        pure (DS.fromList (map fromIntegral is), DS.fromList (map i16ToMaybe fs))
+
+-- | seqFromMTF (Data/MTF/Internal.hs:201-232).
+seqFromMTFW8 :: (Seq Int, Seq (Maybe Word8)) -> Seq (Maybe Word8)
+seqFromMTFW8 (is, fl)
+  | DS.null is || DS.null fl = DS.empty
+  | otherwise = unsafePerformIO $ withB200 $ \ctx -> do
+      let n = DS.length is
+          sg = DS.length fl
+      idx <- pinned (2 * n)
+      fin <- pinned (2 * sg)
+      out <- pinned (2 * n)
+      withForeignPtr idx $ \px -> withForeignPtr fin $ \pf -> withForeignPtr out $ \po -> do
+        forM_ (toList is) $ \i -> when (i < 0 || i > 65535) $ throwIO (ErrorCall "index out of bounds")
+        pokeArray px (map fromIntegral (toList is) :: [Word16])
+        pokeArray pf (map maybeToI16 (toList fl))
+        c_mtf_decode ctx px (fromIntegral n) pf (fromIntegral sg) po >>= check ctx
+        DS.fromList . map i16ToMaybe <$> peekArray n po
+
+-- | seqToRLE (Data/RLE/Internal.hs:104-153) as (count, symbol) runs; the flat
+-- `Seq (Maybe b)` of the reference is @[Just (fromString (show c)), sym]@ per run.
+seqToRLEW8 :: Seq (Maybe Word8) -> Seq (Int, Maybe Word8)
+seqToRLEW8 s
+  | DS.null s = DS.empty
+  | otherwise = unsafePerformIO $ withB200 $ \ctx -> do
+      let n   = DS.length s
+          cap = 2 * n + 1
+      inp <- pinned (2 * n)
+      cnt <- pinned (4 * cap)
+      sym <- pinned (2 * cap)
+      alloca $ \pr -> withForeignPtr inp $ \pi' -> withForeignPtr cnt $ \pc -> withForeignPtr sym $ \ps -> do
+        pokeArray pi' (map maybeToI16 (toList s))
+        c_rle_encode ctx pi' (fromIntegral n) pc ps (fromIntegral cap) pr >>= check ctx
+        r  <- fromIntegral <$> peek pr
+        cs <- peekArray r pc :: IO [Word32]
+        ss <- peekArray r ps
+        pure (DS.fromList (zip (map fromIntegral cs) (map i16ToMaybe ss)))
+
+-- | seqFromRLE (Data/RLE/Internal.hs:155-189) from (count, symbol) runs.
+seqFromRLEW8 :: Seq (Int, Maybe Word8) -> Seq (Maybe Word8)
+seqFromRLEW8 rs
+  | DS.null rs = DS.empty
+  | otherwise  = unsafePerformIO $ withB200 $ \ctx -> do
+      let r = DS.length rs
+      cnt <- pinned (4 * r)
+      sym <- pinned (2 * r)
+      alloca $ \pn -> withForeignPtr cnt $ \pc -> withForeignPtr sym $ \ps -> do
+        pokeArray pc (map (fromIntegral . max 0 . fst) (toList rs) :: [Word32])
+        pokeArray ps (map (maybeToI16 . snd) (toList rs))
+        rc <- c_rle_decode ctx pc ps (fromIntegral r) nullPtr 0 pn      -- sizing call
+        when (rc /= 0 && rc /= tcECap) $ check ctx rc
+        n <- fromIntegral <$> peek pn
+        out <- pinned (2 * n)
+        withForeignPtr out $ \po -> do
+          c_rle_decode ctx pc ps (fromIntegral r) po (fromIntegral n) pn >>= check ctx
+          DS.fromList . map i16ToMaybe <$> peekArray n po
+
+-- | bytestringToBWTToMTFB followed by seqToRLE over the index stream, chained in HBM
+-- (SURVEY.md 8b).  Returns the runs (count, MTF index); tc_block_info carries primary,
+-- sigma and the MTF final list (read it with hsc2hs/offsets in a full binding).
+bwtMtfRleW8 :: BS.ByteString -> Seq (Int, Int)
+bwtMtfRleW8 xs
+  | BS.null xs = DS.empty
+  | otherwise  = unsafePerformIO $ withB200 $ \ctx ->
+      BSU.unsafeUseAsCStringLen xs $ \(p, n) -> do
+        let cap = n + 3
+        cnt  <- pinned (4 * cap)
+        sym  <- pinned (2 * cap)
+        info <- pinned 1024
+        withForeignPtr cnt $ \pc -> withForeignPtr sym $ \ps -> withForeignPtr info $ \pinfo -> do
+          c_bwt_mtf_rle ctx (castPtr p) (fromIntegral n) pc ps (fromIntegral cap) pinfo >>= check ctx
+          -- tc_block_info: n, N, primary (3 x u64), sigma (u32), final_list (257 x i16) = 542 bytes,
+          -- padded to 544; R follows (include/tc_b200.h).  A full binding would use hsc2hs.
+          r  <- fromIntegral <$> (peekByteOff pinfo 544 :: IO Word64)
+          cs <- peekArray r pc :: IO [Word32]
+          ss <- peekArray r ps :: IO [Int16]
+          pure (DS.fromList (zip (map fromIntegral cs) (map fromIntegral ss)))
+
+-- | Device-resident FM-index handle (tc_fm); freed by the GC finaliser.
+newtype B200FM = B200FM (ForeignPtr TcFm)
+
+-- | *ToBWTToFMIndex* (Data/FMIndex.hs:108-183); sa_sample_rate 1 keeps the full SA.
+buildFMIndexW8 :: Int -> BS.ByteString -> B200FM
+buildFMIndexW8 rate xs = unsafePerformIO $ withB200 $ \ctx ->
+  BSU.unsafeUseAsCStringLen xs $ \(p, n) -> alloca $ \pp -> do
+    c_fm_build ctx (castPtr p) (fromIntegral n) (fromIntegral rate) pp >>= check ctx
+    B200FM <$> (peek pp >>= newForeignPtr p_fm_free)
+
+packPatterns :: [BS.ByteString] -> (BS.ByteString, [Word64])
+packPatterns ps = (BS.concat ps, scanl (+) 0 (map (fromIntegral . BS.length) ps))
+
+-- | countFMIndex (Data/FMIndex/Internal.hs:347-438) for a batch; input order is kept.
+countFMIndexW8 :: B200FM -> [BS.ByteString] -> [Maybe Int]
+countFMIndexW8 (B200FM fm) pats = unsafePerformIO $ withB200 $ \ctx -> withForeignPtr fm $ \pfm -> do
+  let (flat, offs) = packPatterns pats
+      q = length pats
+  off <- pinned (8 * (q + 1))
+  out <- pinned (8 * max 1 q)
+  BSU.unsafeUseAsCStringLen flat $ \(pp, _) -> withForeignPtr off $ \po -> withForeignPtr out $ \pc -> do
+    pokeArray po offs
+    c_fm_count ctx pfm (castPtr pp) po (fromIntegral q) pc >>= check ctx
+    map (\c -> if c < 0 then Nothing else Just (fromIntegral c)) <$> (peekArray q pc :: IO [Int64])
+
+-- | locateFMIndex (Data/FMIndex/Internal.hs:448-542) + the rank -> suffixstartpos map of the
+-- wrappers (Data/FMIndex.hs:496): 1-based positions in SA-rank order, per pattern.
+locateFMIndexW8 :: B200FM -> [BS.ByteString] -> [Seq (Maybe Int)]
+locateFMIndexW8 (B200FM fm) pats = unsafePerformIO $ withB200 $ \ctx -> withForeignPtr fm $ \pfm -> do
+  let (flat, offs) = packPatterns pats
+      q = length pats
+  off  <- pinned (8 * (q + 1))
+  hoff <- pinned (8 * (q + 1))
+  BSU.unsafeUseAsCStringLen flat $ \(pp, _) -> withForeignPtr off $ \po -> withForeignPtr hoff $ \ph ->
+    alloca $ \pt -> do
+      pokeArray po offs
+      rc <- c_fm_locate ctx pfm (castPtr pp) po (fromIntegral q) ph nullPtr 0 pt   -- sizing call
+      when (rc /= 0 && rc /= tcECap) $ check ctx rc
+      total <- fromIntegral <$> peek pt
+      pos <- pinned (8 * max 1 total)
+      withForeignPtr pos $ \ppos -> do
+        c_fm_locate ctx pfm (castPtr pp) po (fromIntegral q) ph ppos (fromIntegral total) pt >>= check ctx
+        hs <- map fromIntegral <$> (peekArray (q + 1) ph :: IO [Word64])
+        ps <- map fromIntegral <$> (peekArray total ppos :: IO [Word64])
+        forM (zip hs (tail hs)) $ \(a, b) ->
+          pure (DS.fromList (map Just (take (b - a) (drop a ps))))

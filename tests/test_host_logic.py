@@ -1,0 +1,95 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/tc_b200.h declares,
+host-side value types behave like the reference's, and the product fails loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "tc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from text_compression_b200 import _lib
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    # and the Python binding declares a signature for each of them
+    assert sorted(_lib.EXPORTED_SYMBOLS) == syms
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run (no oracle, no CPU path)."""
+    import torch
+    from text_compression_b200 import _lib, NoDeviceError
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(NoDeviceError):
+        _lib.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "text_compression_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+\S*oracle|liborc|tc_oracle|#include\s+\"[^\"]*oracle", txt, re.M), f
+
+
+def test_value_types():
+    from text_compression_b200.seq import MTF, RLE, MaybeSeq
+    s = MaybeSeq.from_list([b"a", None, b"b"], "B")
+    assert s.codes.tolist() == [97, -1, 98] and s.to_list() == [b"a", None, b"b"]
+    assert s.as_kind("T").to_list() == ["a", None, "b"]
+    assert s == MaybeSeq(np.array([97, -1, 98]), "B") and s != s.as_kind("T")
+    # Q6: the T variants decodeUtf8 every byte on its own -> bytes >= 0x80 throw
+    with pytest.raises(UnicodeDecodeError):
+        MaybeSeq(np.array([0xC3, 0xA9]), "T")
+    r = RLE.from_list([b"4", b"a", b"1", None, b"12", b"c", b"7"], "B")       # odd trailing element ignored
+    assert r.counts.tolist() == [4, 1, 12] and r.syms.tolist() == [97, -1, 99]
+    assert r.to_list() == [b"4", b"a", b"1", None, b"12", b"c"]
+    assert RLE.from_list(["3", "x"], "T").to_list() == ["3", "x"]
+    from text_compression_b200 import FromJustError
+    with pytest.raises(FromJustError):
+        RLE.from_list([None, b"a"], "B")
+    m = MTF(np.array([1, 0]), MaybeSeq.from_list([b"b", None], "B"))
+    assert m.to_tuple() == ([1, 0], [b"b", None])
+
+
+def test_pack_patterns():
+    from text_compression_b200.fmindex import pack_patterns
+    flat, off = pack_patterns([b"abc", "", "de"])
+    assert flat.tobytes() == b"abcde" and off.tolist() == [0, 3, 3, 5]
+    flat, off = pack_patterns([])
+    assert flat.size == 0 and off.tolist() == [0]
+
+
+def test_sharding_helpers():
+    from text_compression_b200 import multi
+    assert multi.blocks_of_rank(10, 4, 1) == [1, 5, 9]
+    cover = sorted(b for r in range(8) for b in multi.blocks_of_rank(512, 8, r))
+    assert cover == list(range(512))
+    for q, ws in ((10, 3), (7, 8), (0, 2), (10_000_000, 8)):
+        sl = [multi.query_slice(q, ws, r) for r in range(ws)]
+        assert sl[0][0] == 0 and sl[-1][1] == q
+        assert all(sl[i][1] == sl[i + 1][0] for i in range(ws - 1))
+        assert max(b - a for a, b in sl) - min(b - a for a, b in sl) <= 1
+
+
+def test_generators_are_deterministic():
+    from tests.util import gen_acgt, gen_acgtn, gen_bytes, gen_reads
+    assert gen_bytes(0xC2, 8).tolist() == gen_bytes(0xC2, 8).tolist()
+    t = gen_acgtn(0xC3, 100000)
+    assert set(np.unique(t).tolist()) <= set(b"ACGTN") and 500 < int((t == ord("N")).sum()) < 1500
+    r = gen_reads(1, gen_acgt(2, 5000), 100, 20)
+    assert r.shape == (100, 20)
