@@ -1,18 +1,26 @@
-// sufsort.cu -- createSuffixArray (src/Data/BWT/Internal.hs:110-134) as a prefix-doubling
-// GPU suffix sort.
+// sufsort.cu -- createSuffixArray (src/Data/BWT/Internal.hs:110-134) as a GPU suffix sort.
 //
 //   1. byte histogram -> alphabet; every symbol gets a code 1..sigma (0 = "past the end",
 //      which is the sentinel: unique and smaller than every symbol, like the empty suffix
-//      sorting first under Ord (Seq a)).
-//   2. initial key of suffix i = its first k symbols packed at b bits each into 64 bits
-//      (b = bits(sigma), k = 64 / b: 21 symbols for ACGT(N), 7 for full bytes).
-//   3. LSD radix sort of (key, i).
-//   4. group heads (key != previous key) -> running max = group id = rank; suffixes in
+//      sorting first under Ord (Seq a)).  The text is re-packed at b = bits(sigma) bits per
+//      symbol, so the key of suffix i (its first k = 64/b symbols: 21 for ACGT(N), 7 for
+//      bytes) is two 64-bit loads and a funnel shift.
+//   2. sort all suffixes by key.  Two paths:
+//      MSD path (balanced inputs): counting sort on a <= 24-bit key prefix with global
+//        atomics (not stable -- it need not be), then every bucket (<= 1024 suffixes) is sorted
+//        by one warp with a bitonic network in shared memory.  ~3 sweeps over the data instead
+//        of 8 LSD passes; the LSD passes are ALU-bound on ballot matching (profiles/README.md).
+//      LSD path (fallback: skewed or very large inputs): 8-bit radix passes (radix.cu).
+//   3. group heads (key != previous key) -> running max = group id = rank; suffixes in
 //      singleton groups are final.
-//   5. while unresolved suffixes remain: compact them, key2 = (group << 32 | rank[i + h]),
-//      radix sort only those, write back, split groups, h *= 2.
+//   4. while unresolved suffixes remain: compact them, key2 = (group << 32 | rank[i + h]),
+//      radix sort only those, write back, split groups, h *= 2.  In the first round rank[i + h]
+//      is found by binary search in the sorted key array, so the inverse suffix array (a 4N-byte
+//      random scatter) is only built if a second round is needed.
 // Suffixes that reach the end of the text inside their first h symbols are always unique,
 // so i + h <= n for every unresolved suffix.
+#include <math.h>
+
 #include <algorithm>
 #include <utility>
 
@@ -43,34 +51,240 @@ __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restric
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
-constexpr int IK_T = 256;
-constexpr int IK_PER = 4;
-constexpr int IK_TILE = IK_T * IK_PER;
-__global__ void __launch_bounds__(IK_T)
-    sa_init_keys_kernel(const uint8_t *__restrict__ t, uint64_t n, uint64_t N, Code256 lut, int b, int k,
-                        uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
-    __shared__ uint16_t codes[IK_TILE + 64];
+// ---- packed text ---------------------------------------------------------------------
+// Symbol j occupies bits [j*b, (j+1)*b) of an MSB-first bit stream of 64-bit words; symbols
+// past the end are 0.  extract_key returns the first kb = k*b bits of suffix i, right-aligned.
+__device__ __forceinline__ uint64_t extract_key(const uint64_t *__restrict__ pw, int b, int kb, uint64_t i) {
+    uint64_t o = i * (uint64_t)b;
+    uint64_t wi = o >> 6;
+    int sh = (int)(o & 63);
+    uint64_t hi = pw[wi], lo = pw[wi + 1];
+    uint64_t v = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+    return v >> (64 - kb);
+}
+
+__global__ void __launch_bounds__(256)
+    sa_pack_kernel(const uint8_t *__restrict__ t, uint64_t n, Code256 lut, int b, uint64_t nwords,
+                   uint64_t *__restrict__ pw) {
     __shared__ uint16_t s_lut[256];
     s_lut[threadIdx.x] = lut.code[threadIdx.x];
     __syncthreads();
-    uint64_t base = (uint64_t)blockIdx.x * IK_TILE;
-    for (int j = threadIdx.x; j < IK_TILE + 64; j += IK_T) {
-        uint64_t i = base + j;
-        codes[j] = i < n ? s_lut[t[i]] : 0;
+    uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (w >= nwords) return;
+    uint64_t bit0 = w * 64;
+    uint64_t word = 0;
+    for (uint64_t j = bit0 / b; j * b < bit0 + 64; j++) {
+        uint64_t code = j < n ? s_lut[t[j]] : 0;
+        int s = 64 - (int)((int64_t)(j * b) - (int64_t)bit0) - b; // left shift that puts the symbol in place
+        word |= s >= 0 ? (code << s) : (code >> (-s));
     }
-    __syncthreads();
-    const uint64_t mask = (b * k >= 64) ? ~0ull : ((1ull << (b * k)) - 1);
-    int o = threadIdx.x * IK_PER;
-    uint64_t key = 0;
-    for (int j = 0; j < k; j++) key = (key << b) | codes[o + j];
-#pragma unroll
-    for (int q = 0; q < IK_PER; q++) {
-        uint64_t p = base + o + q;
-        if (p < N) {
-            keys[p] = key;
-            vals[p] = (uint32_t)p;
+    pw[w] = word;
+}
+
+__global__ void sa_keys_from_packed_kernel(const uint64_t *__restrict__ pw, int b, int kb, uint64_t N,
+                                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    keys[i] = extract_key(pw, b, kb, i);
+    vals[i] = (uint32_t)i;
+}
+
+// ---- MSD path ------------------------------------------------------------------------
+__global__ void msd_hist_kernel(const uint64_t *__restrict__ pw, int b, int kb, int bshift, uint64_t N,
+                                uint32_t *__restrict__ cnt) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    atomicAdd(&cnt[extract_key(pw, b, kb, i) >> bshift], 1u);
+}
+__global__ void msd_max_kernel(const uint32_t *__restrict__ cnt, uint64_t nbk, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbk; i += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, cnt[i]);
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(TC_FULL, m, d));
+    if (lane_id() == 0 && m) atomicMax(out, m);
+}
+// cursor[] = exclusive scan of the counts; after this kernel cursor[bkt] = end of bucket bkt
+__global__ void msd_scatter_kernel(const uint64_t *__restrict__ pw, int b, int kb, int bshift, uint64_t N,
+                                   uint32_t *__restrict__ cursor, uint32_t *__restrict__ sa) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t slot = atomicAdd(&cursor[extract_key(pw, b, kb, i) >> bshift], 1u);
+    sa[slot] = (uint32_t)i;
+}
+
+constexpr int BS_WARPS = 8;
+constexpr int BS_CAP = 512;   // largest bucket one warp sorts
+constexpr int BS_PER = BS_CAP / 32;
+struct BsWarp {
+    uint64_t keys[BS_CAP];
+    uint32_t vals[BS_CAP];
+    uint32_t cnt[256 + 32];
+};
+// bitonic network over (key, suffix) pairs in shared memory: fallback for buckets whose next
+// 8 bits are badly skewed
+__device__ __forceinline__ void warp_bitonic(uint64_t *keys, uint32_t *vals, uint32_t bn) {
+    const unsigned lane = lane_id();
+    uint32_t P = 32;
+    while (P < bn) P <<= 1;
+    for (uint32_t j = bn + lane; j < P; j += 32) {
+        keys[j] = ~0ull;
+        vals[j] = 0xffffffffu;
+    }
+    __syncwarp();
+    for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
+        for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            for (uint32_t idx = lane; idx < P / 2; idx += 32) {
+                uint32_t t = ((idx & ~(j2 - 1)) << 1) | (idx & (j2 - 1));
+                uint32_t p = t | j2;
+                bool up = (t & k2) == 0;
+                uint64_t kt = keys[t], kp = keys[p];
+                uint32_t vt = vals[t], vp = vals[p];
+                bool gt = kt > kp || (kt == kp && vt > vp);
+                if (gt == up) {
+                    keys[t] = kp;
+                    keys[p] = kt;
+                    vals[t] = vp;
+                    vals[p] = vt;
+                }
+            }
+            __syncwarp();
         }
-        key = ((key << b) | codes[o + q + k]) & mask;
+    }
+}
+
+// One warp sorts one bucket [bs, bs+bn) of sa by (key, suffix): stable counting step on the 8
+// key bits that follow the bucket prefix (ballot ranking into warp-private counters, as in the
+// radix scatter), then each sub-bucket -- about one element for balanced text -- is finished by
+// an insertion sort run by the lane that placed its first element.
+__device__ __forceinline__ void warp_bucket_sort(BsWarp &W, uint32_t bs, uint32_t bn, int dshift, uint32_t dmask,
+                                                 const uint64_t *__restrict__ pw, int b, int kb,
+                                                 uint32_t *__restrict__ sa, uint64_t *__restrict__ keys_out) {
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    for (int j = lane; j < 256 + 32; j += 32) W.cnt[j] = 0;
+    __syncwarp();
+    uint64_t key[BS_PER];
+    uint32_t val[BS_PER];
+    uint16_t rnk[BS_PER];
+#pragma unroll
+    for (int i = 0; i < BS_PER; i++) {
+        uint32_t j = lane + 32 * i;
+        val[i] = j < bn ? sa[bs + j] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < BS_PER; i++) {
+        uint32_t j = lane + 32 * i;
+        key[i] = j < bn ? extract_key(pw, b, kb, val[i]) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < BS_PER; i++) {
+        if (32u * i < bn) { // warp-uniform
+            bool valid = lane + 32 * i < bn;
+            uint32_t d = (uint32_t)(key[i] >> dshift) & dmask;
+            unsigned peers = match_bits<8>(d, valid);
+            uint32_t pre = valid ? W.cnt[d] : 0;
+            __syncwarp();
+            if (valid && (peers & lt) == 0) W.cnt[d] = pre + __popc(peers);
+            __syncwarp();
+            rnk[i] = (uint16_t)(pre + __popc(peers & lt));
+        }
+    }
+    // exclusive scan of the 256 counters (8 per lane); cnt[d] becomes the start of sub-bucket d
+    uint32_t c[8], run = 0, mx = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        c[q] = W.cnt[lane * 8 + q];
+        mx = max(mx, c[q]);
+        run += c[q];
+    }
+    uint32_t excl = warp_incl_sum(run) - run;
+    for (int dlt = 16; dlt; dlt >>= 1) mx = max(mx, __shfl_xor_sync(TC_FULL, mx, dlt));
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        W.cnt[lane * 8 + q] = excl;
+        excl += c[q];
+    }
+    if (lane == 31) W.cnt[256] = excl;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < BS_PER; i++) {
+        if (lane + 32 * i < bn) {
+            uint32_t d = (uint32_t)(key[i] >> dshift) & dmask;
+            uint32_t p = W.cnt[d] + rnk[i];
+            W.keys[p] = key[i];
+            W.vals[p] = val[i];
+        }
+    }
+    __syncwarp();
+    if (mx > 24) {
+        warp_bitonic(W.keys, W.vals, bn); // skewed sub-digits: do not let one lane insertion-sort a long run
+    } else if (mx > 1) {
+#pragma unroll
+        for (int i = 0; i < BS_PER; i++) {
+            if (lane + 32 * i < bn && rnk[i] == 0) {
+                uint32_t d = (uint32_t)(key[i] >> dshift) & dmask;
+                uint32_t s0 = W.cnt[d], s1 = W.cnt[d + 1];
+                for (uint32_t x = s0 + 1; x < s1; x++) { // insertion sort of [s0, s1)
+                    uint64_t kx = W.keys[x];
+                    uint32_t vx = W.vals[x];
+                    uint32_t y = x;
+                    while (y > s0 && (W.keys[y - 1] > kx || (W.keys[y - 1] == kx && W.vals[y - 1] > vx))) {
+                        W.keys[y] = W.keys[y - 1];
+                        W.vals[y] = W.vals[y - 1];
+                        y--;
+                    }
+                    W.keys[y] = kx;
+                    W.vals[y] = vx;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    for (uint32_t j = lane; j < bn; j += 32) {
+        sa[bs + j] = W.vals[j];
+        keys_out[bs + j] = W.keys[j];
+    }
+    __syncwarp();
+}
+
+// Warps take groups of 32 consecutive buckets from a global counter (bucket sizes differ and
+// populated bucket ids come in runs, so a static split is badly unbalanced).  Also writes the
+// sorted key of every slot, singletons included.
+__global__ void __launch_bounds__(BS_WARPS * 32)
+    msd_bucket_sort_kernel(const uint32_t *__restrict__ ends, uint64_t nbk, int bshift, const uint64_t *__restrict__ pw,
+                           int b, int kb, uint32_t *__restrict__ sa, uint64_t *__restrict__ keys_out,
+                           unsigned long long *__restrict__ next_group) {
+    extern __shared__ __align__(16) unsigned char bs_raw[];
+    BsWarp &W = reinterpret_cast<BsWarp *>(bs_raw)[threadIdx.x >> 5];
+    const unsigned lane = lane_id();
+    const int dbits = bshift < 8 ? bshift : 8;
+    const int dshift = bshift - dbits;
+    const uint32_t dmask = (1u << dbits) - 1;
+    // work unit: a multiple of 32 bucket ids, sized so that there are ~64K units (one global
+    // atomic per unit; populated ids come in runs, so units must stay much smaller than the table)
+    const uint64_t usz = 32 * (nbk / (32ull * 65536) > 1 ? nbk / (32ull * 65536) : 1);
+    const uint64_t nunits = (nbk + usz - 1) / usz;
+    for (;;) {
+        unsigned long long unit = 0;
+        if (lane == 0) unit = atomicAdd(next_group, 1ull);
+        unit = __shfl_sync(TC_FULL, unit, 0);
+        if (unit >= nunits) break;
+        for (uint64_t base = unit * usz; base < (unit + 1) * usz && base < nbk; base += 32) {
+            uint64_t id = base + lane;
+            uint32_t e = id < nbk ? ends[id] : 0;
+            uint32_t s = __shfl_up_sync(TC_FULL, e, 1);
+            if (lane == 0) s = base ? ends[base - 1] : 0;
+            uint32_t size = id < nbk ? e - s : 0;
+            if (size == 1) keys_out[s] = extract_key(pw, b, kb, sa[s]);
+            unsigned todo = __ballot_sync(TC_FULL, size >= 2);
+            while (todo) {
+                int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                uint32_t bs = __shfl_sync(TC_FULL, s, l), bn = __shfl_sync(TC_FULL, size, l);
+                warp_bucket_sort(W, bs, bn, dshift, dmask, pw, b, kb, sa, keys_out);
+            }
+        }
     }
 }
 
@@ -81,17 +295,43 @@ __global__ void sa_heads_kernel(const uint64_t *__restrict__ keys, uint64_t N, u
     h[j] = (j == 0 || keys[j] != keys[j - 1]) ? (uint32_t)j + 1 : 0u;
 }
 
-// g = running max of h = (group head slot + 1).  rank[sa[j]] = head slot; ns[j] = 1 iff the
-// group of slot j has more than one member.
-__global__ void sa_assign_kernel(const uint32_t *__restrict__ g, const uint32_t *__restrict__ sa, uint64_t N,
-                                 uint32_t *__restrict__ isa, uint32_t *__restrict__ ns) {
+// g = running max of h = (group head slot + 1); ns[j] = 1 iff the group of slot j has more than one member
+__global__ void sa_flags_kernel(const uint32_t *__restrict__ g, uint64_t N, uint32_t *__restrict__ ns) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
-    uint32_t gj = g[j];
-    isa[sa[j]] = gj - 1;
-    bool head = gj == (uint32_t)j + 1;
+    bool head = g[j] == (uint32_t)j + 1;
     bool next_head = (j + 1 == N) || (g[j + 1] == (uint32_t)j + 2);
     ns[j] = (head && next_head) ? 0u : 1u;
+}
+__global__ void sa_build_isa_kernel(const uint32_t *__restrict__ g, const uint32_t *__restrict__ sa, uint64_t N,
+                                    uint32_t *__restrict__ isa) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    isa[sa[j]] = g[j] - 1;
+}
+// first doubling round: rank of suffix s+h = first slot holding its key (binary search in the
+// sorted keys), so no inverse suffix array is needed yet
+__global__ void sa_keys2_lookup_kernel(const uint32_t *__restrict__ cj, uint64_t U, const uint32_t *__restrict__ sa,
+                                       const uint64_t *__restrict__ keys, uint64_t N, const uint32_t *__restrict__ g,
+                                       uint64_t h, uint64_t n, const uint64_t *__restrict__ pw, int b, int kb,
+                                       uint64_t *__restrict__ key2, uint32_t *__restrict__ val2) {
+    uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= U) return;
+    uint32_t j = cj[m];
+    uint32_t s = sa[j];
+    uint64_t x = (uint64_t)s + h;
+    uint32_t r2 = 0;
+    if (x <= n) {
+        uint64_t kx = extract_key(pw, b, kb, x);
+        uint64_t lo = 0, hi = N; // first slot with keys[slot] >= kx
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < kx) lo = mid + 1; else hi = mid;
+        }
+        r2 = (uint32_t)lo;
+    }
+    key2[m] = ((uint64_t)(g[j] - 1) << 32) | r2;
+    val2[m] = s;
 }
 
 __global__ void sa_compact_kernel(const uint32_t *__restrict__ ns, const uint32_t *__restrict__ cpos,
@@ -125,7 +365,7 @@ __global__ void sa_update_kernel(const uint32_t *__restrict__ g2, const uint32_t
     uint32_t headslot = cj[gm - 1];
     uint32_t s = val2s[m];
     sa[slot] = s;
-    isa[s] = headslot;
+    if (isa) isa[s] = headslot;
     g[slot] = headslot + 1;
     bool head = gm == (uint32_t)m + 1;
     bool next_head = (m + 1 == U) || (g2[m + 1] == (uint32_t)m + 2);
@@ -170,45 +410,97 @@ int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t 
     TC_TRY(tc_byte_hist_dev(ctx, d_text, n, hist));
     Code256 lut;
     int sigma = 0;
-    for (int c = 0; c < 256; c++) lut.code[c] = hist[c] ? (uint16_t)(++sigma) : 0;
+    double entropy = 0;
+    for (int c = 0; c < 256; c++) {
+        lut.code[c] = hist[c] ? (uint16_t)(++sigma) : 0;
+        if (hist[c]) {
+            double p = (double)hist[c] / (double)n;
+            entropy -= p * log2(p);
+        }
+    }
     const int b = bits_for((uint64_t)sigma); // codes 0..sigma; 9 bits when all 256 byte values occur
     const int k = 64 / b;
-    const int key_bits = b * k;
-    int shifts[16];
-    int npass = 0;
-    for (int s = 0; s < key_bits; s += 8) shifts[npass++] = s;
+    const int kb = b * k;
+    const unsigned gridN = (unsigned)ceil_div_u64(N, 256);
 
-    uint64_t *k0, *k1;
-    uint32_t *vtmp, *isa, *g, *ns;
-    TC_TRY(ws_alloc(ctx, N, &k0));
-    TC_TRY(ws_alloc(ctx, N, &k1));
-    TC_TRY(ws_alloc(ctx, N, &vtmp));
-    TC_TRY(ws_alloc(ctx, N, &isa));
+    // packed text (+ enough zero symbols behind the end for any key read)
+    const uint64_t nwords = ((N + (uint64_t)k + 64) * (uint64_t)b + 63) / 64 + 2;
+    uint64_t *pw, *keys;
+    uint32_t *g, *ns, *cpos, *d_U;
+    TC_TRY(ws_alloc(ctx, nwords, &pw));
+    TC_TRY(ws_alloc(ctx, N, &keys));
     TC_TRY(ws_alloc(ctx, N, &g));
     TC_TRY(ws_alloc(ctx, N, &ns));
-    // arrange the ping-pong so the sorted values land in d_sa
-    uint32_t *v0 = (npass % 2 == 0) ? d_sa : vtmp;
-    uint32_t *v1 = (npass % 2 == 0) ? vtmp : d_sa;
-    TC_LAUNCH(ctx, sa_init_keys_kernel, (unsigned)ceil_div_u64(N, IK_TILE), IK_T, 0, d_text, n, N, lut,
-              b, k, k0, v0);
-    uint64_t *ks;
-    uint32_t *vs;
-    TC_TRY(tc_radix_sort_pairs(ctx, k0, v0, k1, v1, N, shifts, npass, &ks, &vs));
-    if (vs != d_sa) return TC_E_ARG; // cannot happen
-    const unsigned gridN = (unsigned)ceil_div_u64(N, 256);
-    TC_LAUNCH(ctx, sa_heads_kernel, gridN, 256, 0, ks, N, g);
-    TC_TRY(tc_scan_inclusive_max_u32(ctx, g, g, N));
-    TC_LAUNCH(ctx, sa_assign_kernel, gridN, 256, 0, g, d_sa, N, isa, ns);
-    uint32_t *cpos = (uint32_t *)k0; // keys are dead now; reuse as scratch (N u32 fits in N u64)
-    uint32_t *d_U;
-    TC_TRY(ws_alloc(ctx, 1, &d_U));
-    TC_TRY(tc_scan_exclusive_u32(ctx, ns, cpos, N, d_U));
+    TC_TRY(ws_alloc(ctx, N, &cpos));
+    TC_TRY(ws_alloc(ctx, 2, &d_U));
+    TC_LAUNCH(ctx, sa_pack_kernel, (unsigned)ceil_div_u64(nwords, 256), 256, 0, d_text, n, lut, b, nwords, pw);
     uint32_t *hU = (uint32_t *)ctx->h_scal;
+
+    // ---- sort by key: MSD path when the buckets of a <= 24-bit prefix stay small
+    bool sorted = false;
+    if (N >= 4096) {
+        // prefix length: about N/128 populated buckets, judged by the symbol entropy
+        double want_bits = log2((double)N / 128.0);
+        int p = (int)ceil(want_bits / (entropy > 0.05 ? entropy : 0.05));
+        int pmax = 24 / b;
+        if (p > pmax) p = pmax;
+        if (p > k) p = k;
+        if (p < 1) p = 1;
+        const int PB = p * b;
+        const int bshift = kb - PB;
+        const uint64_t nbk = 1ull << PB;
+        uint32_t *cnt;
+        TC_TRY(ws_alloc(ctx, nbk, &cnt));
+        TC_CUDA(cudaMemsetAsync(cnt, 0, nbk * sizeof(uint32_t), ctx->stream));
+        TC_CUDA(cudaMemsetAsync(d_U, 0, 2 * sizeof(uint32_t), ctx->stream));
+        TC_LAUNCH(ctx, msd_hist_kernel, gridN, 256, 0, pw, b, kb, bshift, N, cnt);
+        unsigned mgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(nbk, 256), (uint64_t)ctx->sm_count * 8);
+        TC_LAUNCH(ctx, msd_max_kernel, mgrid, 256, 0, cnt, nbk, d_U);
+        TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (hU[0] <= (uint32_t)BS_CAP) {
+            TC_TRY(tc_scan_exclusive_u32(ctx, cnt, cnt, nbk, (uint32_t *)nullptr));
+            TC_LAUNCH(ctx, msd_scatter_kernel, gridN, 256, 0, pw, b, kb, bshift, N, cnt, d_sa);
+            const size_t bs_smem = sizeof(BsWarp) * BS_WARPS;
+            TC_CUDA(cudaFuncSetAttribute(msd_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bs_smem));
+            unsigned long long *d_next;
+            TC_TRY(ws_alloc(ctx, 1, &d_next));
+            TC_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
+            unsigned sgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(nbk, BS_WARPS * 32), (uint64_t)ctx->sm_count * 3);
+            TC_LAUNCH(ctx, msd_bucket_sort_kernel, sgrid, BS_WARPS * 32, bs_smem, cnt, nbk, bshift, pw, b, kb, d_sa, keys,
+                      d_next);
+            sorted = true;
+        }
+    }
+    if (!sorted) { // LSD path
+        int shifts[16];
+        int npass = 0;
+        for (int s = 0; s < kb; s += 8) shifts[npass++] = s;
+        uint64_t *k1;
+        uint32_t *vtmp;
+        TC_TRY(ws_alloc(ctx, N, &k1));
+        TC_TRY(ws_alloc(ctx, N, &vtmp));
+        // arrange the ping-pong so the sorted values land in d_sa and the sorted keys in `keys`
+        uint64_t *ka = (npass % 2 == 0) ? keys : k1, *kbuf = (npass % 2 == 0) ? k1 : keys;
+        uint32_t *v0 = (npass % 2 == 0) ? d_sa : vtmp, *v1 = (npass % 2 == 0) ? vtmp : d_sa;
+        TC_LAUNCH(ctx, sa_keys_from_packed_kernel, gridN, 256, 0, pw, b, kb, N, ka, v0);
+        uint64_t *ks;
+        uint32_t *vs;
+        TC_TRY(tc_radix_sort_pairs(ctx, ka, v0, kbuf, v1, N, shifts, npass, &ks, &vs));
+        if (vs != d_sa || ks != keys) return TC_E_ARG; // cannot happen
+    }
+
+    // ---- groups and unresolved suffixes
+    TC_LAUNCH(ctx, sa_heads_kernel, gridN, 256, 0, keys, N, g);
+    TC_TRY(tc_scan_inclusive_max_u32(ctx, g, g, N));
+    TC_LAUNCH(ctx, sa_flags_kernel, gridN, 256, 0, g, N, ns);
+    TC_TRY(tc_scan_exclusive_u32(ctx, ns, cpos, N, d_U));
     TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t U = hU[0];
     if (U > 0) {
-        uint32_t *cjA, *cjB, *val2a, *val2b, *g2, *ns2, *cpos2;
+        uint32_t *cjA, *cjB, *val2a, *val2b, *g2, *ns2, *cpos2, *isa = nullptr;
         uint64_t *key2a, *key2b;
         TC_TRY(ws_alloc(ctx, U, &cjA));
         TC_TRY(ws_alloc(ctx, U, &cjB));
@@ -232,7 +524,16 @@ int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t 
                 return TC_E_CUDA;
             }
             const unsigned gridU = (unsigned)ceil_div_u64(U, 256);
-            TC_LAUNCH(ctx, sa_keys2_kernel, gridU, 256, 0, cjA, U, d_sa, isa, g, h, n, key2a, val2a);
+            if (round == 0) {
+                TC_LAUNCH(ctx, sa_keys2_lookup_kernel, gridU, 256, 0, cjA, U, d_sa, keys, N, g, h, n, pw, b, kb, key2a,
+                          val2a);
+            } else {
+                if (!isa) { // second round: now the inverse suffix array pays for itself
+                    TC_TRY(ws_alloc(ctx, N, &isa));
+                    TC_LAUNCH(ctx, sa_build_isa_kernel, gridN, 256, 0, g, d_sa, N, isa);
+                }
+                TC_LAUNCH(ctx, sa_keys2_kernel, gridU, 256, 0, cjA, U, d_sa, isa, g, h, n, key2a, val2a);
+            }
             uint64_t *k2s;
             uint32_t *v2s;
             TC_TRY(tc_radix_sort_pairs(ctx, key2a, val2a, key2b, val2b, U, sh2, np2, &k2s, &v2s));
