@@ -152,17 +152,20 @@ __device__ __forceinline__ void warp_bitonic(uint64_t *keys, uint32_t *vals, uin
     }
 }
 
-// One warp sorts one bucket [bs, bs+bn) of sa by (key, suffix): stable counting step on the 8
-// key bits that follow the bucket prefix (ballot ranking into warp-private counters, as in the
-// radix scatter), then each sub-bucket -- about one element for balanced text -- is finished by
-// an insertion sort run by the lane that placed its first element.
-__device__ __forceinline__ void warp_bucket_sort(BsWarp &W, uint32_t bs, uint32_t bn, int dshift, uint32_t dmask,
+// One warp sorts one bucket [bs, bs+bn) of sa by (key, suffix).  The keys of a bucket share
+// their prefix; the `fbits` key bits below it are sorted by 1 or 2 stable counting rounds of 8
+// bits (LSD; ballot ranking into warp-private counters, as in the radix scatter).  What is
+// left are short runs of equal field -- about one element for balanced text -- finished by an
+// insertion sort run by the lane that owns the run head.  Badly skewed buckets fall back to a
+// bitonic network.
+__device__ __forceinline__ void warp_bucket_sort(BsWarp &W, uint32_t bs, uint32_t bn, int bshift, int nrounds,
                                                  const uint64_t *__restrict__ pw, int b, int kb,
-                                                 uint32_t *__restrict__ sa, uint64_t *__restrict__ keys_out) {
+                                                 uint32_t *__restrict__ sa, uint32_t *__restrict__ ties) {
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
-    for (int j = lane; j < 256 + 32; j += 32) W.cnt[j] = 0;
-    __syncwarp();
+    const int fbits = bshift < 8 * nrounds ? bshift : 8 * nrounds;
+    const int fshift = bshift - fbits;
+    const int nr = (fbits + 7) / 8;
     uint64_t key[BS_PER];
     uint32_t val[BS_PER];
     uint16_t rnk[BS_PER];
@@ -176,91 +179,142 @@ __device__ __forceinline__ void warp_bucket_sort(BsWarp &W, uint32_t bs, uint32_
         uint32_t j = lane + 32 * i;
         key[i] = j < bn ? extract_key(pw, b, kb, val[i]) : 0;
     }
-#pragma unroll
-    for (int i = 0; i < BS_PER; i++) {
-        if (32u * i < bn) { // warp-uniform
-            bool valid = lane + 32 * i < bn;
-            uint32_t d = (uint32_t)(key[i] >> dshift) & dmask;
-            unsigned peers = match_bits<8>(d, valid);
-            uint32_t pre = valid ? W.cnt[d] : 0;
-            __syncwarp();
-            if (valid && (peers & lt) == 0) W.cnt[d] = pre + __popc(peers);
-            __syncwarp();
-            rnk[i] = (uint16_t)(pre + __popc(peers & lt));
+    if (nr == 0) { // the prefix is the whole key: nothing to count on
+        for (uint32_t j = lane; j < bn; j += 32) {
+            W.keys[j] = key[j >> 5];
+            W.vals[j] = val[j >> 5];
         }
     }
-    // exclusive scan of the 256 counters (8 per lane); cnt[d] becomes the start of sub-bucket d
-    uint32_t c[8], run = 0, mx = 0;
+    for (int r = 0; r < nr; r++) {
+        const int dsh = fshift + 8 * r;
+        if (r > 0) { // re-read in the order the previous round produced
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        c[q] = W.cnt[lane * 8 + q];
-        mx = max(mx, c[q]);
-        run += c[q];
-    }
-    uint32_t excl = warp_incl_sum(run) - run;
-    for (int dlt = 16; dlt; dlt >>= 1) mx = max(mx, __shfl_xor_sync(TC_FULL, mx, dlt));
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        W.cnt[lane * 8 + q] = excl;
-        excl += c[q];
-    }
-    if (lane == 31) W.cnt[256] = excl;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < BS_PER; i++) {
-        if (lane + 32 * i < bn) {
-            uint32_t d = (uint32_t)(key[i] >> dshift) & dmask;
-            uint32_t p = W.cnt[d] + rnk[i];
-            W.keys[p] = key[i];
-            W.vals[p] = val[i];
+            for (int i = 0; i < BS_PER; i++) {
+                uint32_t j = lane + 32 * i;
+                if (j < bn) {
+                    key[i] = W.keys[j];
+                    val[i] = W.vals[j];
+                }
+            }
         }
-    }
-    __syncwarp();
-    if (mx > 24) {
-        warp_bitonic(W.keys, W.vals, bn); // skewed sub-digits: do not let one lane insertion-sort a long run
-    } else if (mx > 1) {
+        for (int j = lane; j < 256 + 32; j += 32) W.cnt[j] = 0;
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < BS_PER; i++) {
-            if (lane + 32 * i < bn && rnk[i] == 0) {
-                uint32_t d = (uint32_t)(key[i] >> dshift) & dmask;
-                uint32_t s0 = W.cnt[d], s1 = W.cnt[d + 1];
-                for (uint32_t x = s0 + 1; x < s1; x++) { // insertion sort of [s0, s1)
-                    uint64_t kx = W.keys[x];
-                    uint32_t vx = W.vals[x];
-                    uint32_t y = x;
-                    while (y > s0 && (W.keys[y - 1] > kx || (W.keys[y - 1] == kx && W.vals[y - 1] > vx))) {
-                        W.keys[y] = W.keys[y - 1];
-                        W.vals[y] = W.vals[y - 1];
-                        y--;
-                    }
-                    W.keys[y] = kx;
-                    W.vals[y] = vx;
-                }
+            if (32u * i < bn) { // warp-uniform
+                bool valid = lane + 32 * i < bn;
+                uint32_t d = (uint32_t)(key[i] >> dsh) & 255u;
+                unsigned peers = match_bits<8>(d, valid);
+                uint32_t pre = valid ? W.cnt[d] : 0;
+                __syncwarp();
+                if (valid && (peers & lt) == 0) W.cnt[d] = pre + __popc(peers);
+                __syncwarp();
+                rnk[i] = (uint16_t)(pre + __popc(peers & lt));
+            }
+        }
+        // exclusive scan of the 256 counters (8 per lane); cnt[d] becomes the start of digit d
+        uint32_t c[8], run = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            c[q] = W.cnt[lane * 8 + q];
+            run += c[q];
+        }
+        uint32_t excl = warp_incl_sum(run) - run;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            W.cnt[lane * 8 + q] = excl;
+            excl += c[q];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < BS_PER; i++) {
+            if (lane + 32 * i < bn) {
+                uint32_t d = (uint32_t)(key[i] >> dsh) & 255u;
+                uint32_t p = W.cnt[d] + rnk[i];
+                W.keys[p] = key[i];
+                W.vals[p] = val[i];
             }
         }
         __syncwarp();
     }
+    // Runs of equal field are short (about one element for balanced text).  Every element counts
+    // the members of its run that are smaller than itself and moves straight to its final slot;
+    // all lanes walk outwards together, so there is no divergence.  A run longer than 32 means
+    // the bucket is badly skewed: fall back to the bitonic network.
+    uint32_t newpos[BS_PER];
+    bool fallback = false;
+#pragma unroll
+    for (int i = 0; i < BS_PER; i++) {
+        if (32u * i < bn) { // warp-uniform
+            const uint32_t j = lane + 32 * i;
+            const bool valid = j < bn;
+            const uint64_t kj = valid ? W.keys[j] : 0;
+            const uint32_t vj = valid ? W.vals[j] : 0;
+            const uint64_t fj = kj >> fshift;
+            key[i] = kj;
+            val[i] = vj;
+            uint32_t nleft = 0, nless = 0;
+            bool goL = valid, goR = valid;
+            for (uint32_t d = 1;; d++) {
+                bool l = goL && j >= d;
+                uint64_t kl = l ? W.keys[j - d] : 0;
+                l = l && (kl >> fshift) == fj;
+                goL = l;
+                bool r = goR && j + d < bn;
+                uint64_t kr = r ? W.keys[j + d] : 0;
+                r = r && (kr >> fshift) == fj;
+                goR = r;
+                if (!__any_sync(TC_FULL, l || r)) break;
+                if (d > 32) {
+                    fallback = true;
+                    break;
+                }
+                if (l) {
+                    nleft++;
+                    nless += (kl < kj) || (kl == kj && W.vals[j - d] < vj);
+                }
+                if (r) nless += (kr < kj) || (kr == kj && W.vals[j + d] < vj);
+            }
+            newpos[i] = j - nleft + nless;
+        }
+    }
+    fallback = __any_sync(TC_FULL, fallback);
+    __syncwarp();
+    if (!fallback) {
+#pragma unroll
+        for (int i = 0; i < BS_PER; i++) {
+            if (lane + 32 * i < bn) {
+                W.keys[newpos[i]] = key[i];
+                W.vals[newpos[i]] = val[i];
+            }
+        }
+        __syncwarp();
+    } else {
+        warp_bitonic(W.keys, W.vals, bn);
+    }
+    // suffixes whose key equals a neighbour's are unresolved (equal keys never span buckets)
+    uint32_t tied = 0;
     for (uint32_t j = lane; j < bn; j += 32) {
         sa[bs + j] = W.vals[j];
-        keys_out[bs + j] = W.keys[j];
+        uint64_t kj = W.keys[j];
+        tied += (j > 0 && W.keys[j - 1] == kj) || (j + 1 < bn && W.keys[j + 1] == kj);
     }
+    for (int dlt = 16; dlt; dlt >>= 1) tied += __shfl_xor_sync(TC_FULL, tied, dlt);
+    if (lane == 0 && tied) atomicAdd(ties, tied);
     __syncwarp();
 }
 
 // Warps take groups of 32 consecutive buckets from a global counter (bucket sizes differ and
-// populated bucket ids come in runs, so a static split is badly unbalanced).  Also writes the
-// sorted key of every slot, singletons included.
+// populated bucket ids come in runs, so a static split is badly unbalanced).  *ties counts the
+// suffixes that still share their key with a neighbour.
 __global__ void __launch_bounds__(BS_WARPS * 32)
-    msd_bucket_sort_kernel(const uint32_t *__restrict__ ends, uint64_t nbk, int bshift, const uint64_t *__restrict__ pw,
-                           int b, int kb, uint32_t *__restrict__ sa, uint64_t *__restrict__ keys_out,
+    msd_bucket_sort_kernel(const uint32_t *__restrict__ ends, uint64_t nbk, int bshift, int nrounds,
+                           const uint64_t *__restrict__ pw, int b, int kb, uint32_t *__restrict__ sa, uint32_t *__restrict__ ties,
                            unsigned long long *__restrict__ next_group) {
     extern __shared__ __align__(16) unsigned char bs_raw[];
     BsWarp &W = reinterpret_cast<BsWarp *>(bs_raw)[threadIdx.x >> 5];
     const unsigned lane = lane_id();
-    const int dbits = bshift < 8 ? bshift : 8;
-    const int dshift = bshift - dbits;
-    const uint32_t dmask = (1u << dbits) - 1;
     // work unit: a multiple of 32 bucket ids, sized so that there are ~64K units (one global
     // atomic per unit; populated ids come in runs, so units must stay much smaller than the table)
     const uint64_t usz = 32 * (nbk / (32ull * 65536) > 1 ? nbk / (32ull * 65536) : 1);
@@ -276,16 +330,22 @@ __global__ void __launch_bounds__(BS_WARPS * 32)
             uint32_t s = __shfl_up_sync(TC_FULL, e, 1);
             if (lane == 0) s = base ? ends[base - 1] : 0;
             uint32_t size = id < nbk ? e - s : 0;
-            if (size == 1) keys_out[s] = extract_key(pw, b, kb, sa[s]);
             unsigned todo = __ballot_sync(TC_FULL, size >= 2);
             while (todo) {
                 int l = __ffs(todo) - 1;
                 todo &= todo - 1;
                 uint32_t bs = __shfl_sync(TC_FULL, s, l), bn = __shfl_sync(TC_FULL, size, l);
-                warp_bucket_sort(W, bs, bn, dshift, dmask, pw, b, kb, sa, keys_out);
+                warp_bucket_sort(W, bs, bn, bshift, nrounds, pw, b, kb, sa, ties);
             }
         }
     }
+}
+
+__global__ void sa_gather_keys_kernel(const uint64_t *__restrict__ pw, int b, int kb, const uint32_t *__restrict__ sa,
+                                      uint64_t N, uint64_t *__restrict__ keys) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    keys[j] = extract_key(pw, b, kb, sa[j]);
 }
 
 // h[j] = j+1 if slot j starts a new group (key differs from its predecessor), else 0
@@ -425,13 +485,9 @@ int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t 
 
     // packed text (+ enough zero symbols behind the end for any key read)
     const uint64_t nwords = ((N + (uint64_t)k + 64) * (uint64_t)b + 63) / 64 + 2;
-    uint64_t *pw, *keys;
+    uint64_t *pw, *keys = nullptr;
     uint32_t *g, *ns, *cpos, *d_U;
     TC_TRY(ws_alloc(ctx, nwords, &pw));
-    TC_TRY(ws_alloc(ctx, N, &keys));
-    TC_TRY(ws_alloc(ctx, N, &g));
-    TC_TRY(ws_alloc(ctx, N, &ns));
-    TC_TRY(ws_alloc(ctx, N, &cpos));
     TC_TRY(ws_alloc(ctx, 2, &d_U));
     TC_LAUNCH(ctx, sa_pack_kernel, (unsigned)ceil_div_u64(nwords, 256), 256, 0, d_text, n, lut, b, nwords, pw);
     uint32_t *hU = (uint32_t *)ctx->h_scal;
@@ -468,12 +524,26 @@ int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t 
             TC_TRY(ws_alloc(ctx, 1, &d_next));
             TC_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
             unsigned sgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(nbk, BS_WARPS * 32), (uint64_t)ctx->sm_count * 3);
-            TC_LAUNCH(ctx, msd_bucket_sort_kernel, sgrid, BS_WARPS * 32, bs_smem, cnt, nbk, bshift, pw, b, kb, d_sa, keys,
-                      d_next);
+            TC_CUDA(cudaMemsetAsync(d_U, 0, sizeof(uint32_t), ctx->stream));
+            // key bits needed below the prefix to split a bucket into singletons, judged by the symbol
+            // entropy per key bit: one counting round of 8 bits or two
+            double ebit = (entropy > 0.05 ? entropy : 0.05) / (double)b;
+            int nrounds = (log2((double)(hU[0] > 1 ? hU[0] : 2)) / ebit > 10.0) ? 2 : 1;
+            TC_LAUNCH(ctx, msd_bucket_sort_kernel, sgrid, BS_WARPS * 32, bs_smem, cnt, nbk, bshift, nrounds, pw, b, kb,
+                      d_sa, d_U, d_next);
+            TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            TC_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (hU[0] == 0) { // every suffix is already distinguished by its key: done
+                tc_ws_release(ctx, mk);
+                return TC_OK;
+            }
+            TC_TRY(ws_alloc(ctx, N, &keys));
+            TC_LAUNCH(ctx, sa_gather_keys_kernel, gridN, 256, 0, pw, b, kb, d_sa, N, keys);
             sorted = true;
         }
     }
     if (!sorted) { // LSD path
+        TC_TRY(ws_alloc(ctx, N, &keys));
         int shifts[16];
         int npass = 0;
         for (int s = 0; s < kb; s += 8) shifts[npass++] = s;
@@ -492,6 +562,9 @@ int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t 
     }
 
     // ---- groups and unresolved suffixes
+    TC_TRY(ws_alloc(ctx, N, &g));
+    TC_TRY(ws_alloc(ctx, N, &ns));
+    TC_TRY(ws_alloc(ctx, N, &cpos));
     TC_LAUNCH(ctx, sa_heads_kernel, gridN, 256, 0, keys, N, g);
     TC_TRY(tc_scan_inclusive_max_u32(ctx, g, g, N));
     TC_LAUNCH(ctx, sa_flags_kernel, gridN, 256, 0, g, N, ns);
