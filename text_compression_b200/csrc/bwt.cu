@@ -31,6 +31,11 @@ __global__ void bwt_emit_kernel(const uint8_t *__restrict__ t, const uint32_t *_
     if (sa1) sa1[j] = s + 1;
 }
 
+__global__ void sa_plus1_kernel(const uint32_t *__restrict__ sa, uint64_t N, uint32_t *__restrict__ sa1) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) sa1[j] = sa[j] + 1;
+}
+
 struct CodeU8 {
     const uint8_t *p;
     uint64_t primary;
@@ -230,12 +235,17 @@ int bwt_encode_dev_impl(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t 
     uint64_t *d_primary;
     TC_TRY(ws_alloc(ctx, N, &d_sa));
     TC_TRY(ws_alloc(ctx, 1, &d_primary));
-    TC_TRY(tc_suffix_sort_dev(ctx, d_text, n, d_sa));
-    TC_LAUNCH(ctx, bwt_emit_kernel, (unsigned)ceil_div_u64(N, 256), 256, 0, d_text, d_sa, N, d_bwt, d_primary,
-              d_sa_1based);
-    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_primary, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    *primary = ctx->h_scal[0];
+    bool done = false;
+    TC_TRY(tc_suffix_sort_bwt_dev(ctx, d_text, n, d_sa, d_bwt, primary, &done));
+    if (done && d_sa_1based) {
+        TC_LAUNCH(ctx, sa_plus1_kernel, (unsigned)ceil_div_u64(N, 256), 256, 0, d_sa, N, d_sa_1based);
+    } else if (!done) {
+        TC_LAUNCH(ctx, bwt_emit_kernel, (unsigned)ceil_div_u64(N, 256), 256, 0, d_text, d_sa, N, d_bwt, d_primary,
+                  d_sa_1based);
+        TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_primary, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        *primary = ctx->h_scal[0];
+    }
     tc_ws_release(ctx, mk);
     return TC_OK;
 }

@@ -30,6 +30,7 @@ struct tc_ctx {
     // pinned scalars for small device->host results
     uint64_t *h_scal = nullptr; // 1024 x u64, pinned
     uint64_t launches = 0;
+    bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     char err[512] = {0};
     // optional per-kernel timing (tc_ctx_profile): one event pair per launch
     struct ProfRec {
@@ -111,6 +112,9 @@ int tc_scan_exclusive_u64(tc_ctx *ctx, const uint64_t *in, uint64_t *out, uint64
 int tc_scan_inclusive_max_u32(tc_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n);
 // suffix array of text$ (0-based start positions, N = n+1 entries) in d_sa
 int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_sa);
+// same, and when d_bwt is given the fast path also emits the BWT bytes + primary (*bwt_done)
+int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint8_t *d_bwt,
+                           uint64_t *primary, bool *bwt_done);
 
 // ---- device helpers --------------------------------------------------------------
 #ifdef __CUDACC__

@@ -1,4 +1,6 @@
 // ctx.cu -- context lifecycle, scratch arena, pinned host memory, error strings.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static const size_t kAlign = 512;
@@ -38,6 +40,8 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     tc_ctx *ctx = new tc_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    const char *nm = getenv("TC_B200_NO_MSD");
+    ctx->no_msd = nm && nm[0] == '1';
     if (have_stream) {
         ctx->stream = stream;
         ctx->own_stream = false;

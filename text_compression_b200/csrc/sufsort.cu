@@ -89,130 +89,431 @@ __global__ void sa_keys_from_packed_kernel(const uint64_t *__restrict__ pw, int 
     vals[i] = (uint32_t)i;
 }
 
-// ---- MSD path ------------------------------------------------------------------------
-__global__ void msd_hist_kernel(const uint64_t *__restrict__ pw, int b, int kb, int bshift, uint64_t N,
-                                uint32_t *__restrict__ cnt) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    atomicAdd(&cnt[extract_key(pw, b, kb, i) >> bshift], 1u);
-}
-__global__ void msd_max_kernel(const uint32_t *__restrict__ cnt, uint64_t nbk, uint32_t *__restrict__ out) {
-    uint32_t m = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbk; i += (uint64_t)gridDim.x * blockDim.x)
-        m = max(m, cnt[i]);
-    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(TC_FULL, m, d));
-    if (lane_id() == 0 && m) atomicMax(out, m);
-}
-// cursor[] = exclusive scan of the counts; after this kernel cursor[bkt] = end of bucket bkt
-__global__ void msd_scatter_kernel(const uint64_t *__restrict__ pw, int b, int kb, int bshift, uint64_t N,
-                                   uint32_t *__restrict__ cursor, uint32_t *__restrict__ sa) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    uint32_t slot = atomicAdd(&cursor[extract_key(pw, b, kb, i) >> bshift], 1u);
-    sa[slot] = (uint32_t)i;
+// ---- MSD path on uniform keys ---------------------------------------------------------
+// ukey(i): a 32-bit order-preserving code of suffix i's key -- the arithmetic code of its
+// first symbols under the text's own symbol frequencies (looked up g symbols at a time).
+// key(s) <= key(t) implies ukey(s) <= ukey(t), and for memoryless text ukey is uniform on
+// [0, 2^32) whatever the alphabet or its skew, so plain bit fields of ukey are balanced
+// radix digits: no sparse bucket ids (ACGTN in 3-bit codes fills 5/8 of each digit), no
+// entropy guessing.  Ties in ukey are settled with the full 63-bit keys.
+struct SymProb {
+    float p[258]; // p[code], code 0 = past the end
+};
+
+// lut[e] = cum16 << 16 | freq16 over all g-grams e in numeric (= lexicographic) order
+__global__ void __launch_bounds__(1024) uk_lut_kernel(SymProb sp, int sigma, int b, int g, uint32_t *__restrict__ lut) {
+    __shared__ uint32_t sh[1024 / 32 + 1];
+    const uint32_t E = 1u << (g * b);
+    float nvalid = 1.f;
+    for (int j = 0; j < g; j++) nvalid *= (float)(sigma + 1);
+    const float S = 65536.f - nvalid - 64.f;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < E; base += 1024) {
+        uint32_t e = base + threadIdx.x;
+        float pr = e < E ? 1.f : 0.f;
+        for (int j = 0; j < g; j++) {
+            uint32_t c = (e >> (b * (g - 1 - j))) & ((1u << b) - 1);
+            pr *= c <= (uint32_t)sigma ? sp.p[c] : 0.f;
+        }
+        uint32_t f = 0;
+        if (pr > 0.f) {
+            f = (uint32_t)(pr * S);
+            if (f < 1) f = 1;
+        }
+        uint32_t tot;
+        uint32_t cum = carry + block_excl_sum<uint32_t, 1024>(f, sh, &tot);
+        if (e < E) {
+            if (cum > 65535u) {
+                cum = 65535u;
+                f = 0;
+            }
+            if (cum + f > 65536u) f = 65536u - cum;
+            if (f > 65535u) f = 65535u;
+            lut[e] = (cum << 16) | f;
+        }
+        carry += tot;
+    }
 }
 
-constexpr int BS_WARPS = 8;
-constexpr int BS_CAP = 512;   // largest bucket one warp sorts
-constexpr int BS_PER = BS_CAP / 32;
-struct BsWarp {
-    uint64_t keys[BS_CAP];
-    uint32_t vals[BS_CAP];
-    uint32_t cnt[256 + 32];
-};
-// bitonic network over (key, suffix) pairs in shared memory: fallback for buckets whose next
-// 8 bits are badly skewed
-__device__ __forceinline__ void warp_bitonic(uint64_t *keys, uint32_t *vals, uint32_t bn) {
+__device__ __forceinline__ uint32_t ukey_of(uint64_t key, int kb, int gb, int G, const uint32_t *__restrict__ lut) {
+    uint32_t x = 0, r = 0xffffffffu;
+    int sh = kb - gb;
+    const uint32_t m = (1u << gb) - 1;
+    for (int j = 0; j < G; j++, sh -= gb) {
+        uint32_t e = __ldg(&lut[(uint32_t)(key >> sh) & m]);
+        x += __umulhi(r, e & 0xffff0000u);
+        r = __umulhi(r, e << 16);
+    }
+    return x;
+}
+
+// bytes of a uint4 summed (each field of the result holds at most 16 * 255)
+__device__ __forceinline__ uint32_t byte_sum16(uint4 v) {
+    uint32_t a = (v.x & 0x00ff00ffu) + ((v.x >> 8) & 0x00ff00ffu);
+    a += (v.y & 0x00ff00ffu) + ((v.y >> 8) & 0x00ff00ffu);
+    a += (v.z & 0x00ff00ffu) + ((v.z >> 8) & 0x00ff00ffu);
+    a += (v.w & 0x00ff00ffu) + ((v.w >> 8) & 0x00ff00ffu);
+    return (a & 0xffffu) + (a >> 16);
+}
+
+// Counting without atomics or matching: every lane owns a byte counter per digit
+// (cnt[digit][lane], 8 KB per warp), bumped with a plain load/add/store; a lane sees at most
+// PC_ITEMS keys per tile, so a byte is enough.  The warp then sums its 32 columns per digit.
+constexpr int PC_T = 256;
+constexpr int PC_WARPS = PC_T / 32;
+constexpr int PC_ITEMS = 64;
+constexpr int PC_TILE = PC_T * PC_ITEMS;
+constexpr int PC_WCHUNK = 32 * PC_ITEMS; // keys per warp
+constexpr size_t PC_SMEM = (size_t)PC_WARPS * 256 * 32;
+
+__device__ __forceinline__ void pc_zero(uint8_t *wc, unsigned lane) {
+    uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int q = 0; q < 16; q++) reinterpret_cast<uint4 *>(wc)[q * 32 + lane] = z;
+}
+// total of digit d = q*32 + lane over the warp's 32 lane columns
+__device__ __forceinline__ uint32_t pc_total(const uint8_t *wc, int q, unsigned lane) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(wc + (q * 32 + lane) * 32);
+    return byte_sum16(p[0]) + byte_sum16(p[1]);
+}
+
+// K_A: ukey of every suffix 0..n-1 + histogram of the level-1 digit
+__global__ void __launch_bounds__(PC_T)
+    uk_keys_kernel(const uint64_t *__restrict__ pw, int b, int kb, int gb, int G, const uint32_t *__restrict__ lut,
+                   uint64_t n, int shift1, uint32_t *__restrict__ ukey, uint32_t *__restrict__ hist1) {
+    extern __shared__ __align__(16) uint8_t pc_cnt[];
+    __shared__ uint16_t wtot[PC_WARPS][256];
+    const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
-    uint32_t P = 32;
-    while (P < bn) P <<= 1;
-    for (uint32_t j = bn + lane; j < P; j += 32) {
-        keys[j] = ~0ull;
-        vals[j] = 0xffffffffu;
+    uint8_t *wc = pc_cnt + (size_t)w * 8192;
+    pc_zero(wc, lane);
+    __syncwarp();
+    const uint64_t tbase = (uint64_t)blockIdx.x * PC_TILE + (uint64_t)w * PC_WCHUNK;
+#pragma unroll 4
+    for (int r = 0; r < PC_ITEMS; r++) {
+        uint64_t i = tbase + (uint64_t)r * 32 + lane;
+        if (i < n) {
+            uint32_t u = ukey_of(extract_key(pw, b, kb, i), kb, gb, G, lut);
+            ukey[i] = u;
+            uint32_t d = shift1 < 32 ? u >> shift1 : 0u;
+            wc[d * 32 + lane]++;
+        }
     }
     __syncwarp();
-    for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
-        for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-            for (uint32_t idx = lane; idx < P / 2; idx += 32) {
-                uint32_t t = ((idx & ~(j2 - 1)) << 1) | (idx & (j2 - 1));
-                uint32_t p = t | j2;
-                bool up = (t & k2) == 0;
-                uint64_t kt = keys[t], kp = keys[p];
-                uint32_t vt = vals[t], vp = vals[p];
-                bool gt = kt > kp || (kt == kp && vt > vp);
-                if (gt == up) {
-                    keys[t] = kp;
-                    keys[p] = kt;
-                    vals[t] = vp;
-                    vals[p] = vt;
-                }
-            }
-            __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) wtot[w][q * 32 + lane] = (uint16_t)pc_total(wc, q, lane);
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int ww = 0; ww < PC_WARPS; ww++) s += wtot[ww][threadIdx.x];
+    if (s) atomicAdd(&hist1[threadIdx.x], s);
+}
+
+// Partition tiles never straddle a segment (= a bucket of the previous level).  tilebase[s]
+// = first tile of segment s, chunkbase[s] = first counting chunk of segment s.
+constexpr int PT_T = 256;
+constexpr int PT_ITEMS = 16;
+constexpr int PT_TILE = PT_T * PT_ITEMS;
+constexpr int PT_WARPS = PT_T / 32;
+
+// one CTA: segment starts from the level-1 histogram, + tile and chunk tables for level 2
+__global__ void __launch_bounds__(256)
+    seg_tables_kernel(const uint32_t *__restrict__ hist1, int nseg, uint32_t *__restrict__ segstart /*nseg+1*/,
+                      uint32_t *__restrict__ cursor1, uint32_t *__restrict__ tilebase /*nseg+1*/,
+                      uint32_t *__restrict__ chunkbase /*nseg+1*/) {
+    __shared__ uint32_t sh[256 / 32 + 1];
+    const int s = threadIdx.x;
+    uint32_t c = s < nseg ? hist1[s] : 0;
+    uint32_t tot;
+    uint32_t ex = block_excl_sum<uint32_t, 256>(c, sh, &tot);
+    if (s < nseg) {
+        segstart[s] = ex;
+        cursor1[s] = ex;
+    }
+    if (s == 0) segstart[nseg] = tot;
+    uint32_t t = (c + PT_TILE - 1) / PT_TILE;
+    ex = block_excl_sum<uint32_t, 256>(t, sh, &tot);
+    if (s < nseg) tilebase[s] = ex;
+    if (s == 0) tilebase[nseg] = tot;
+    uint32_t h = (c + PC_WCHUNK - 1) / PC_WCHUNK;
+    ex = block_excl_sum<uint32_t, 256>(h, sh, &tot);
+    if (s < nseg) chunkbase[s] = ex;
+    if (s == 0) chunkbase[nseg] = tot;
+}
+
+// segment of unit t: base[s] <= t < base[s+1]   (base[nseg] = number of units)
+__device__ __forceinline__ int seg_of(const uint32_t *__restrict__ base, int nseg, uint32_t t) {
+    int lo = 0, hi = nseg;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (base[mid] <= t) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// level-2 histogram: one warp per chunk of a segment, hist2[seg * nb2 + digit]
+__global__ void __launch_bounds__(PC_T)
+    seg_hist_kernel(const uint2 *__restrict__ rec, const uint32_t *__restrict__ segstart,
+                    const uint32_t *__restrict__ chunkbase, int nseg, int shift, uint32_t dmask,
+                    uint32_t *__restrict__ hist2) {
+    extern __shared__ __align__(16) uint8_t pc_cnt[];
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const uint32_t c = blockIdx.x * PC_WARPS + w;
+    if (c >= chunkbase[nseg]) return;
+    const int s = seg_of(chunkbase, nseg, c);
+    const uint32_t beg = segstart[s] + (c - chunkbase[s]) * PC_WCHUNK;
+    const uint32_t end = min(segstart[s + 1], beg + PC_WCHUNK);
+    uint8_t *wc = pc_cnt + (size_t)w * 8192;
+    pc_zero(wc, lane);
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < PC_ITEMS; r++) {
+        uint32_t i = beg + r * 32 + lane;
+        if (i < end) {
+            uint32_t d = (rec[i].x >> shift) & dmask;
+            wc[d * 32 + lane]++;
+        }
+    }
+    __syncwarp();
+    const uint32_t nb = dmask + 1;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        uint32_t d = q * 32 + lane;
+        if (d < nb) {
+            uint32_t t = pc_total(wc, q, lane);
+            if (t) atomicAdd(&hist2[(uint32_t)s * nb + d], t);
         }
     }
 }
 
-// One warp sorts one bucket [bs, bs+bn) of sa by (key, suffix).  The keys of a bucket share
-// their prefix; the `fbits` key bits below it are sorted by 1 or 2 stable counting rounds of 8
-// bits (LSD; ballot ranking into warp-private counters, as in the radix scatter).  What is
-// left are short runs of equal field -- about one element for balanced text -- finished by an
-// insertion sort run by the lane that owns the run head.  Badly skewed buckets fall back to a
-// bitonic network.
-__device__ __forceinline__ void warp_bucket_sort(BsWarp &W, uint32_t bs, uint32_t bn, int bshift, int nrounds,
-                                                 const uint64_t *__restrict__ pw, int b, int kb,
-                                                 uint32_t *__restrict__ sa, uint32_t *__restrict__ ties) {
+// level-2 bucket starts: one CTA per segment scans the segment's digit counts
+__global__ void __launch_bounds__(256)
+    starts_kernel(const uint32_t *__restrict__ hist2, const uint32_t *__restrict__ segstart, uint32_t nb2,
+                  uint32_t nbk, uint64_t n, uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t sh[256 / 32 + 1];
+    const uint32_t s = blockIdx.x, d = threadIdx.x;
+    uint32_t c = d < nb2 ? hist2[s * nb2 + d] : 0;
+    uint32_t ex = segstart[s] + block_excl_sum<uint32_t, 256>(c, sh, (uint32_t *)nullptr);
+    if (d < nb2) {
+        starts[s * nb2 + d] = ex;
+        cursor[s * nb2 + d] = ex;
+    }
+    if (s == 0 && d == 0) starts[nbk] = (uint32_t)n;
+}
+
+struct PtSmem {
+    uint2 stage[PT_TILE];
+    uint16_t wcount[PT_WARPS][256];
+    uint16_t dig_start[256];
+    uint32_t gbase[256];
+    uint32_t scan[PT_T / 32 + 1];
+};
+
+// One partition level.  In-tile ranking by warp match groups into warp-private counters (as
+// in radix.cu), records staged in digit order, then written as runs; the tile's slice of every
+// bucket is reserved with one atomicAdd on the bucket cursor (placement inside a bucket need
+// not be deterministic -- the final sort orders it).
+// FIRST: the input is ukey[i]; the record becomes (ukey, i | T[i-1] << 24) when packprev.
+template <bool FIRST>
+__global__ void __launch_bounds__(PT_T, 4)
+    part_kernel(const uint32_t *__restrict__ ukey_in, const uint8_t *__restrict__ text, int packprev,
+                const uint2 *__restrict__ rec_in, uint2 *__restrict__ rec_out, uint64_t n, int shift, uint32_t dmask,
+                const uint32_t *__restrict__ segstart, const uint32_t *__restrict__ tilebase, int nseg,
+                uint32_t *__restrict__ cursor) {
+    extern __shared__ __align__(16) unsigned char pt_raw[];
+    PtSmem &S = *reinterpret_cast<PtSmem *>(pt_raw);
+    const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
-    const int fbits = bshift < 8 * nrounds ? bshift : 8 * nrounds;
-    const int fshift = bshift - fbits;
-    const int nr = (fbits + 7) / 8;
-    uint64_t key[BS_PER];
-    uint32_t val[BS_PER];
-    uint16_t rnk[BS_PER];
+    uint32_t beg, end, seg = 0;
+    if (FIRST) {
+        beg = blockIdx.x * PT_TILE;
+        end = (uint32_t)min((uint64_t)beg + PT_TILE, n);
+    } else {
+        if (blockIdx.x >= tilebase[nseg]) return;
+        seg = (uint32_t)seg_of(tilebase, nseg, blockIdx.x);
+        beg = segstart[seg] + (blockIdx.x - tilebase[seg]) * PT_TILE;
+        end = min(segstart[seg + 1], beg + PT_TILE);
+    }
+    const uint32_t cnt = end - beg;
+    for (int j = threadIdx.x; j < PT_WARPS * 256 / 2; j += PT_T) reinterpret_cast<uint32_t *>(&S.wcount[0][0])[j] = 0;
+    __syncthreads();
+    uint32_t key[PT_ITEMS];
+    uint32_t rnk[PT_ITEMS / 2]; // two 16-bit ranks per register
 #pragma unroll
-    for (int i = 0; i < BS_PER; i++) {
-        uint32_t j = lane + 32 * i;
-        val[i] = j < bn ? sa[bs + j] : 0;
+    for (int r = 0; r < PT_ITEMS; r++) {
+        uint32_t j = w * (32 * PT_ITEMS) + r * 32 + lane;
+        key[r] = 0;
+        if (j < cnt) key[r] = FIRST ? ukey_in[beg + j] : rec_in[beg + j].x;
     }
 #pragma unroll
-    for (int i = 0; i < BS_PER; i++) {
-        uint32_t j = lane + 32 * i;
-        key[i] = j < bn ? extract_key(pw, b, kb, val[i]) : 0;
+    for (int r = 0; r < PT_ITEMS; r++) {
+        uint32_t j = w * (32 * PT_ITEMS) + r * 32 + lane;
+        bool valid = j < cnt;
+        uint32_t d = (key[r] >> shift) & dmask;
+        unsigned peers = match_bits<8>(d, valid);
+        uint32_t pre = valid ? S.wcount[w][d] : 0;
+        __syncwarp();
+        if (valid && (peers & lt) == 0) S.wcount[w][d] = (uint16_t)(pre + __popc(peers));
+        __syncwarp();
+        uint32_t rk = pre + __popc(peers & lt);
+        rnk[r >> 1] = (r & 1) ? (rnk[r >> 1] | (rk << 16)) : rk;
     }
-    if (nr == 0) { // the prefix is the whole key: nothing to count on
-        for (uint32_t j = lane; j < bn; j += 32) {
-            W.keys[j] = key[j >> 5];
-            W.vals[j] = val[j >> 5];
+    __syncthreads();
+    {
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < PT_WARPS; ww++) {
+            uint32_t t = S.wcount[ww][d];
+            S.wcount[ww][d] = (uint16_t)run;
+            run += t;
+        }
+        uint32_t total;
+        uint32_t ex = block_excl_sum<uint32_t, PT_T>(run, S.scan, &total);
+        S.dig_start[d] = (uint16_t)ex;
+        uint32_t g = run ? atomicAdd(&cursor[seg * (dmask + 1) + d], run) : 0u;
+        S.gbase[d] = g - ex; // global slot of local slot 0 of digit d
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PT_ITEMS; r++) {
+        uint32_t j = w * (32 * PT_ITEMS) + r * 32 + lane;
+        if (j < cnt) {
+            // the second word is fetched only now (keeps the ranking phase's register footprint small)
+            uint32_t i = beg + j, y;
+            if (FIRST) y = (packprev && i) ? (i | ((uint32_t)text[i - 1] << 24)) : i;
+            else y = rec_in[i].y;
+            uint32_t d = (key[r] >> shift) & dmask;
+            S.stage[(uint32_t)S.dig_start[d] + S.wcount[w][d] + ((rnk[r >> 1] >> (16 * (r & 1))) & 0xffffu)] =
+                make_uint2(key[r], y);
         }
     }
-    for (int r = 0; r < nr; r++) {
-        const int dsh = fshift + 8 * r;
-        if (r > 0) { // re-read in the order the previous round produced
-#pragma unroll
-            for (int i = 0; i < BS_PER; i++) {
-                uint32_t j = lane + 32 * i;
-                if (j < bn) {
-                    key[i] = W.keys[j];
-                    val[i] = W.vals[j];
-                }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < cnt; p += PT_T) {
+        uint2 v = S.stage[p];
+        rec_out[S.gbase[(v.x >> shift) & dmask] + p] = v;
+    }
+}
+
+// Final level: one warp sorts one bucket (<= FS_CAP records) by the low `rb` bits of ukey.
+// Elements are (field << 9 | local index) in one word, so an LSD round moves 4 bytes per
+// record; 8-bit rounds, stable ranking by match groups.  Records whose field ties with a
+// neighbour are ordered by their full keys (rare: about N^2 / 2^33 pairs).
+constexpr int FS_WARPS = 8;
+constexpr int FS_CAP = 512;
+constexpr int FS_PER = FS_CAP / 32;
+struct FsWarp {
+    uint32_t e[FS_CAP];
+    uint32_t v[FS_CAP];
+    uint16_t cnt[256];
+};
+enum { FL_TIES = 0, FL_OVERFLOW = 1 };
+
+// Order of two suffixes whose first k symbols agree: compare the following keys, k symbols at
+// a time.  A suffix that runs past the end reads as zeros, which no symbol code equals, so two
+// different suffixes always differ at some step; only very long repeats exhaust `steps`.
+// returns -1 / +1, or 0 if still undecided
+__device__ __noinline__ int suffix_cmp_deep(const uint64_t *__restrict__ pw, int b, int kb, int k, uint64_t n,
+                                               uint64_t i, uint64_t j, int steps) {
+    for (int s = 1; s <= steps; s++) {
+        uint64_t pi = i + (uint64_t)s * k, pj = j + (uint64_t)s * k;
+        uint64_t a = pi <= n ? extract_key(pw, b, kb, pi) : 0ull;
+        uint64_t c = pj <= n ? extract_key(pw, b, kb, pj) : 0ull;
+        if (a != c) return a < c ? -1 : 1;
+    }
+    return 0;
+}
+
+// Slow path of the final sort: the calling lane insertion-sorts, by full suffix comparison,
+// every run of equal field whose head sits at one of its slots (lane, lane+32, ...).  Runs are
+// disjoint, so lanes never touch each other's slots.  Returns undecided pairs | overflow << 16.
+__device__ __noinline__ uint32_t fs_sort_runs(uint32_t *we, const uint32_t *wv, uint32_t M, unsigned lane,
+                                              const uint64_t *__restrict__ pw, int b, int kb, int k, uint64_t n,
+                                              uint32_t idxmask) {
+    uint32_t undecided = 0, overflow = 0;
+    for (uint32_t a = lane; a + 1 < M; a += 32) {
+        const uint32_t f = we[a] >> 9;
+        if ((we[a + 1] >> 9) != f || (a > 0 && (we[a - 1] >> 9) == f)) continue;
+        uint32_t c = a + 2;
+        while (c < M && (we[c] >> 9) == f) c++;
+        if (c - a > 64) { // a long repeat: leave it to the general path
+            overflow = 1;
+            continue;
+        }
+        for (uint32_t x = a + 1; x < c; x++) {
+            const uint32_t ex = we[x], sx = wv[ex & 511u] & idxmask;
+            const uint64_t kx = extract_key(pw, b, kb, sx);
+            uint32_t y = x;
+            while (y > a) {
+                const uint32_t ey = we[y - 1], sy = wv[ey & 511u] & idxmask;
+                const uint64_t ky = extract_key(pw, b, kb, sy);
+                int cmp = ky < kx ? -1 : (ky > kx ? 1 : suffix_cmp_deep(pw, b, kb, k, n, sy, sx, 16));
+                undecided += cmp == 0;
+                if (cmp <= 0) break;
+                we[y] = ey;
+                y--;
             }
+            we[y] = ex;
         }
-        for (int j = lane; j < 256 + 32; j += 32) W.cnt[j] = 0;
+    }
+    return (undecided > 0xffffu ? 0xffffu : undecided) | (overflow << 16);
+}
+
+__global__ void __launch_bounds__(FS_WARPS * 32, 4)
+    final_sort_kernel(const uint2 *__restrict__ rec, const uint32_t *__restrict__ starts, uint32_t nbuckets, int rb,
+                      const uint64_t *__restrict__ pw, int b, int kb, int k, uint64_t n, int packprev,
+                      const uint8_t *__restrict__ text, uint32_t *__restrict__ sa, uint8_t *__restrict__ bwt,
+                      uint64_t *__restrict__ primary, uint32_t *__restrict__ flags) {
+    __shared__ FsWarp fs[FS_WARPS];
+    FsWarp &W = fs[threadIdx.x >> 5];
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t bk = blockIdx.x * FS_WARPS + (threadIdx.x >> 5);
+    if (bk >= nbuckets) return;
+    const uint32_t s = starts[bk], M = starts[bk + 1] - s;
+    if (M == 0) return;
+    if (M > FS_CAP) {
+        if (lane == 0) atomicOr(&flags[FL_OVERFLOW], 1u);
+        return;
+    }
+    // field = the top fbits of the rb remaining bits (all of them unless rb > 23)
+    const int fbits = rb < 23 ? rb : 23;
+    const int fsh = rb - fbits;
+    const uint32_t fmask = (fbits ? (0xffffffffu >> (32 - fbits)) : 0u);
+    uint32_t e[FS_PER];
+    uint32_t rnk[FS_PER / 2]; // two 16-bit ranks per register
+#pragma unroll
+    for (int i = 0; i < FS_PER; i++) {
+        uint32_t j = lane + 32 * i;
+        e[i] = 0;
+        if (j < M) {
+            uint2 r = rec[s + j];
+            W.v[j] = r.y;
+            e[i] = (((r.x >> fsh) & fmask) << 9) | j;
+        }
+    }
+    const int nr = (fbits + 7) / 8;
+    for (int round = 0; round < nr; round++) {
+        const int dsh = 9 + 8 * round;
+        for (int j = lane; j < 128; j += 32) reinterpret_cast<uint32_t *>(W.cnt)[j] = 0;
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < BS_PER; i++) {
-            if (32u * i < bn) { // warp-uniform
-                bool valid = lane + 32 * i < bn;
-                uint32_t d = (uint32_t)(key[i] >> dsh) & 255u;
+        for (int i = 0; i < FS_PER; i++) {
+            if (32u * i < M) { // warp-uniform
+                bool valid = lane + 32 * i < M;
+                uint32_t d = (e[i] >> dsh) & 255u;
                 unsigned peers = match_bits<8>(d, valid);
                 uint32_t pre = valid ? W.cnt[d] : 0;
                 __syncwarp();
-                if (valid && (peers & lt) == 0) W.cnt[d] = pre + __popc(peers);
+                if (valid && (peers & lt) == 0) W.cnt[d] = (uint16_t)(pre + __popc(peers));
                 __syncwarp();
-                rnk[i] = (uint16_t)(pre + __popc(peers & lt));
+                uint32_t rk = pre + __popc(peers & lt);
+                rnk[i >> 1] = (i & 1) ? (rnk[i >> 1] | (rk << 16)) : rk;
             }
         }
-        // exclusive scan of the 256 counters (8 per lane); cnt[d] becomes the start of digit d
+        // exclusive scan of the 256 counters, 8 per lane
         uint32_t c[8], run = 0;
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -223,121 +524,64 @@ __device__ __forceinline__ void warp_bucket_sort(BsWarp &W, uint32_t bs, uint32_
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            W.cnt[lane * 8 + q] = excl;
+            W.cnt[lane * 8 + q] = (uint16_t)excl;
             excl += c[q];
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < BS_PER; i++) {
-            if (lane + 32 * i < bn) {
-                uint32_t d = (uint32_t)(key[i] >> dsh) & 255u;
-                uint32_t p = W.cnt[d] + rnk[i];
-                W.keys[p] = key[i];
-                W.vals[p] = val[i];
-            }
+        for (int i = 0; i < FS_PER; i++) {
+            if (lane + 32 * i < M) W.e[W.cnt[(e[i] >> dsh) & 255u] + ((rnk[i >> 1] >> (16 * (i & 1))) & 0xffffu)] = e[i];
         }
         __syncwarp();
-    }
-    // Runs of equal field are short (about one element for balanced text).  Every element counts
-    // the members of its run that are smaller than itself and moves straight to its final slot;
-    // all lanes walk outwards together, so there is no divergence.  A run longer than 32 means
-    // the bucket is badly skewed: fall back to the bitonic network.
-    uint32_t newpos[BS_PER];
-    bool fallback = false;
 #pragma unroll
-    for (int i = 0; i < BS_PER; i++) {
-        if (32u * i < bn) { // warp-uniform
-            const uint32_t j = lane + 32 * i;
-            const bool valid = j < bn;
-            const uint64_t kj = valid ? W.keys[j] : 0;
-            const uint32_t vj = valid ? W.vals[j] : 0;
-            const uint64_t fj = kj >> fshift;
-            key[i] = kj;
-            val[i] = vj;
-            uint32_t nleft = 0, nless = 0;
-            bool goL = valid, goR = valid;
-            for (uint32_t d = 1;; d++) {
-                bool l = goL && j >= d;
-                uint64_t kl = l ? W.keys[j - d] : 0;
-                l = l && (kl >> fshift) == fj;
-                goL = l;
-                bool r = goR && j + d < bn;
-                uint64_t kr = r ? W.keys[j + d] : 0;
-                r = r && (kr >> fshift) == fj;
-                goR = r;
-                if (!__any_sync(TC_FULL, l || r)) break;
-                if (d > 32) {
-                    fallback = true;
-                    break;
-                }
-                if (l) {
-                    nleft++;
-                    nless += (kl < kj) || (kl == kj && W.vals[j - d] < vj);
-                }
-                if (r) nless += (kr < kj) || (kr == kj && W.vals[j + d] < vj);
-            }
-            newpos[i] = j - nleft + nless;
+        for (int i = 0; i < FS_PER; i++) {
+            uint32_t j = lane + 32 * i;
+            if (j < M) e[i] = W.e[j];
         }
     }
-    fallback = __any_sync(TC_FULL, fallback);
-    __syncwarp();
-    if (!fallback) {
+    if (nr == 0) {
 #pragma unroll
-        for (int i = 0; i < BS_PER; i++) {
-            if (lane + 32 * i < bn) {
-                W.keys[newpos[i]] = key[i];
-                W.vals[newpos[i]] = val[i];
-            }
-        }
+        for (int i = 0; i < FS_PER; i++)
+            if (lane + 32 * i < M) W.e[lane + 32 * i] = e[i];
         __syncwarp();
-    } else {
-        warp_bitonic(W.keys, W.vals, bn);
     }
-    // suffixes whose key equals a neighbour's are unresolved (equal keys never span buckets)
-    uint32_t tied = 0;
-    for (uint32_t j = lane; j < bn; j += 32) {
-        sa[bs + j] = W.vals[j];
-        uint64_t kj = W.keys[j];
-        tied += (j > 0 && W.keys[j - 1] == kj) || (j + 1 < bn && W.keys[j + 1] == kj);
+    // runs of equal field (rare): the lane holding the head of a run sorts it by full keys
+    bool head = false;
+#pragma unroll
+    for (int i = 0; i < FS_PER; i++) {
+        uint32_t j = lane + 32 * i;
+        if (j + 1 < M) {
+            uint32_t f = e[i] >> 9;
+            head |= (W.e[j + 1] >> 9) == f && (j == 0 || (W.e[j - 1] >> 9) != f);
+        }
     }
-    for (int dlt = 16; dlt; dlt >>= 1) tied += __shfl_xor_sync(TC_FULL, tied, dlt);
-    if (lane == 0 && tied) atomicAdd(ties, tied);
-    __syncwarp();
+    if (__any_sync(TC_FULL, head)) {
+        uint32_t r = 0;
+        if (head) r = fs_sort_runs(W.e, W.v, M, lane, pw, b, kb, k, n, packprev ? 0x00ffffffu : 0xffffffffu);
+        __syncwarp();
+        uint32_t und = r & 0xffffu;
+        for (int dlt = 16; dlt; dlt >>= 1) und += __shfl_xor_sync(TC_FULL, und, dlt);
+        if (lane == 0 && und) atomicAdd(&flags[FL_TIES], und);
+        if (r >> 16) atomicOr(&flags[FL_OVERFLOW], 1u);
+    }
+    // slot 0 of the suffix array belongs to the empty suffix, so bucket slot j is row 1 + s + j
+    for (uint32_t j = lane; j < M; j += 32) {
+        uint32_t v = W.v[W.e[j] & 511u];
+        uint32_t idx = packprev ? (v & 0x00ffffffu) : v;
+        sa[1 + s + j] = idx;
+        if (bwt) {
+            uint8_t c = packprev ? (uint8_t)(v >> 24) : (idx ? text[idx - 1] : (uint8_t)0);
+            bwt[1 + s + j] = c;
+            if (idx == 0) *primary = 1ull + s + j;
+        }
+    }
 }
 
-// Warps take groups of 32 consecutive buckets from a global counter (bucket sizes differ and
-// populated bucket ids come in runs, so a static split is badly unbalanced).  *ties counts the
-// suffixes that still share their key with a neighbour.
-__global__ void __launch_bounds__(BS_WARPS * 32)
-    msd_bucket_sort_kernel(const uint32_t *__restrict__ ends, uint64_t nbk, int bshift, int nrounds,
-                           const uint64_t *__restrict__ pw, int b, int kb, uint32_t *__restrict__ sa, uint32_t *__restrict__ ties,
-                           unsigned long long *__restrict__ next_group) {
-    extern __shared__ __align__(16) unsigned char bs_raw[];
-    BsWarp &W = reinterpret_cast<BsWarp *>(bs_raw)[threadIdx.x >> 5];
-    const unsigned lane = lane_id();
-    // work unit: a multiple of 32 bucket ids, sized so that there are ~64K units (one global
-    // atomic per unit; populated ids come in runs, so units must stay much smaller than the table)
-    const uint64_t usz = 32 * (nbk / (32ull * 65536) > 1 ? nbk / (32ull * 65536) : 1);
-    const uint64_t nunits = (nbk + usz - 1) / usz;
-    for (;;) {
-        unsigned long long unit = 0;
-        if (lane == 0) unit = atomicAdd(next_group, 1ull);
-        unit = __shfl_sync(TC_FULL, unit, 0);
-        if (unit >= nunits) break;
-        for (uint64_t base = unit * usz; base < (unit + 1) * usz && base < nbk; base += 32) {
-            uint64_t id = base + lane;
-            uint32_t e = id < nbk ? ends[id] : 0;
-            uint32_t s = __shfl_up_sync(TC_FULL, e, 1);
-            if (lane == 0) s = base ? ends[base - 1] : 0;
-            uint32_t size = id < nbk ? e - s : 0;
-            unsigned todo = __ballot_sync(TC_FULL, size >= 2);
-            while (todo) {
-                int l = __ffs(todo) - 1;
-                todo &= todo - 1;
-                uint32_t bs = __shfl_sync(TC_FULL, s, l), bn = __shfl_sync(TC_FULL, size, l);
-                warp_bucket_sort(W, bs, bn, bshift, nrounds, pw, b, kb, sa, ties);
-            }
-        }
+__global__ void sa_row0_kernel(const uint8_t *__restrict__ t, uint64_t n, uint32_t *__restrict__ sa,
+                               uint8_t *__restrict__ bwt) {
+    if (threadIdx.x == 0) {
+        sa[0] = (uint32_t)n;
+        if (bwt) bwt[0] = t[n - 1];
     }
 }
 
@@ -459,7 +703,16 @@ int tc_byte_hist_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *h
 }
 
 int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_sa) {
+    return tc_suffix_sort_bwt_dev(ctx, d_text, n, d_sa, nullptr, nullptr, nullptr);
+}
+
+// Suffix array + (optionally) the BWT in the same sweep: when d_bwt is given and the fast path
+// resolves every suffix, the last level writes the BWT bytes and the primary index itself and
+// *bwt_done is set; otherwise the caller emits the BWT from d_sa.
+int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint8_t *d_bwt,
+                           uint64_t *primary /*host*/, bool *bwt_done) {
     const uint64_t N = n + 1;
+    if (bwt_done) *bwt_done = false;
     if (N >= 0xfffffffeull) return TC_E_TOOBIG;
     if (n == 0) {
         TC_CUDA(cudaMemsetAsync(d_sa, 0, sizeof(uint32_t), ctx->stream));
@@ -492,54 +745,95 @@ int tc_suffix_sort_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t 
     TC_LAUNCH(ctx, sa_pack_kernel, (unsigned)ceil_div_u64(nwords, 256), 256, 0, d_text, n, lut, b, nwords, pw);
     uint32_t *hU = (uint32_t *)ctx->h_scal;
 
-    // ---- sort by key: MSD path when the buckets of a <= 24-bit prefix stay small
+    // ---- sort by key: MSD path on uniform keys (two partition levels + per-warp final sort)
     bool sorted = false;
-    if (N >= 4096) {
-        // prefix length: about N/128 populated buckets, judged by the symbol entropy
-        double want_bits = log2((double)N / 128.0);
-        int p = (int)ceil(want_bits / (entropy > 0.05 ? entropy : 0.05));
-        int pmax = 24 / b;
-        if (p > pmax) p = pmax;
-        if (p > k) p = k;
-        if (p < 1) p = 1;
-        const int PB = p * b;
-        const int bshift = kb - PB;
-        const uint64_t nbk = 1ull << PB;
-        uint32_t *cnt;
-        TC_TRY(ws_alloc(ctx, nbk, &cnt));
-        TC_CUDA(cudaMemsetAsync(cnt, 0, nbk * sizeof(uint32_t), ctx->stream));
-        TC_CUDA(cudaMemsetAsync(d_U, 0, 2 * sizeof(uint32_t), ctx->stream));
-        TC_LAUNCH(ctx, msd_hist_kernel, gridN, 256, 0, pw, b, kb, bshift, N, cnt);
-        unsigned mgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(nbk, 256), (uint64_t)ctx->sm_count * 8);
-        TC_LAUNCH(ctx, msd_max_kernel, mgrid, 256, 0, cnt, nbk, d_U);
-        TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bwt_done) *bwt_done = false;
+    if (n >= 4096 && n <= (25ull << 20) && !ctx->no_msd) {
+        int PB = 0;
+        while (PB < 16 && (n >> PB) > 256) PB++;
+        const int B1 = PB < 8 ? PB : 8, B2 = PB - B1;
+        const int nb1 = 1 << B1, nb2 = 1 << B2;
+        const uint32_t nbk = 1u << PB;
+        const int packprev = (d_bwt && n <= (1ull << 24)) ? 1 : 0;
+        // lookups of g symbols each; enough of them to spend the 32 bits of ukey
+        int gs = 12 / b;
+        if (gs < 1) gs = 1;
+        if (gs > k) gs = k;
+        const int gb = gs * b;
+        int G = (int)ceil(34.0 / ((double)gs * (entropy > 0.02 ? entropy : 0.02)));
+        if (G > k / gs) G = k / gs;
+        if (G < 1) G = 1;
+        SymProb sp;
+        memset(&sp, 0, sizeof sp);
+        sp.p[0] = 1.0f / (float)N;
+        for (int c = 0; c < 256; c++)
+            if (hist[c]) sp.p[lut.code[c]] = (float)((double)hist[c] / (double)N);
+        uint32_t *uk_lut, *ukey, *hist1, *hist2, *segstart, *cursor1, *tilebase, *chunkbase, *starts2, *cursor2, *flags;
+        uint2 *recA, *recB = nullptr;
+        uint64_t *d_primary = nullptr;
+        if (d_bwt) TC_TRY(ws_alloc(ctx, 1, &d_primary));
+        TC_TRY(ws_alloc(ctx, (size_t)1 << gb, &uk_lut));
+        TC_TRY(ws_alloc(ctx, n, &ukey));
+        TC_TRY(ws_alloc(ctx, 256 + (size_t)nbk + 8, &hist1)); // hist1 | hist2 | flags: one memset
+        hist2 = hist1 + 256;
+        flags = hist2 + nbk;
+        TC_TRY(ws_alloc(ctx, 257, &segstart));
+        TC_TRY(ws_alloc(ctx, 256, &cursor1));
+        TC_TRY(ws_alloc(ctx, 257, &tilebase));
+        TC_TRY(ws_alloc(ctx, 257, &chunkbase));
+        TC_TRY(ws_alloc(ctx, (size_t)nbk + 1, &starts2));
+        TC_TRY(ws_alloc(ctx, (size_t)nbk, &cursor2));
+        TC_TRY(ws_alloc(ctx, n, &recA));
+        if (B2) TC_TRY(ws_alloc(ctx, n, &recB));
+        TC_CUDA(cudaMemsetAsync(hist1, 0, (256 + (size_t)nbk + 8) * sizeof(uint32_t), ctx->stream));
+        TC_CUDA(cudaFuncSetAttribute(uk_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(seg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+        TC_CUDA(cudaFuncSetAttribute(part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
+        TC_CUDA(cudaFuncSetAttribute(part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
+        TC_LAUNCH(ctx, uk_lut_kernel, 1, 1024, 0, sp, sigma, b, gs, uk_lut);
+        ctx->prof_bytes_next = n + 4 * n;
+        TC_LAUNCH(ctx, uk_keys_kernel, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut, n,
+                  32 - B1, ukey, hist1);
+        TC_LAUNCH(ctx, seg_tables_kernel, 1, 256, 0, hist1, nb1, segstart, cursor1, tilebase, chunkbase);
+        ctx->prof_bytes_next = 4 * n + (packprev ? n : 0) + 8 * n;
+        TC_LAUNCH(ctx, part_kernel<true>, (unsigned)ceil_div_u64(n, PT_TILE), PT_T, sizeof(PtSmem), ukey, d_text, packprev,
+                  (const uint2 *)nullptr, recA, n, 32 - B1, (uint32_t)(nb1 - 1), (const uint32_t *)nullptr,
+                  (const uint32_t *)nullptr, 1, cursor1);
+        const uint2 *recF = recA;
+        const uint32_t *startsF = segstart;
+        if (B2) {
+            ctx->prof_bytes_next = 8 * n;
+            TC_LAUNCH(ctx, seg_hist_kernel, (unsigned)ceil_div_u64(ceil_div_u64(n, PC_WCHUNK) + nb1, PC_WARPS), PC_T,
+                      PC_SMEM, recA, segstart, chunkbase, nb1, 32 - PB, (uint32_t)(nb2 - 1), hist2);
+            TC_LAUNCH(ctx, starts_kernel, nb1, 256, 0, hist2, segstart, (uint32_t)nb2, nbk, n, starts2, cursor2);
+            ctx->prof_bytes_next = 16 * n;
+            TC_LAUNCH(ctx, part_kernel<false>, (unsigned)(ceil_div_u64(n, PT_TILE) + nb1), PT_T, sizeof(PtSmem),
+                      (const uint32_t *)nullptr, (const uint8_t *)nullptr, 0, (const uint2 *)recA, recB, n, 32 - PB,
+                      (uint32_t)(nb2 - 1), segstart, tilebase, nb1, cursor2);
+            recF = recB;
+            startsF = starts2;
+        }
+        // the empty suffix sorts first (row 0); its BWT symbol is the last text symbol
+        TC_LAUNCH(ctx, sa_row0_kernel, 1, 32, 0, d_text, n, d_sa, d_bwt);
+        ctx->prof_bytes_next = 8 * n + 4 * n + (d_bwt ? n : 0);
+        TC_LAUNCH(ctx, final_sort_kernel, (unsigned)ceil_div_u64(nbk, FS_WARPS), FS_WARPS * 32, 0, recF, startsF, nbk,
+                  32 - PB, pw, b, kb, k, n, packprev, d_text, d_sa, d_bwt, d_primary, flags);
+        TC_CUDA(cudaMemcpyAsync(hU, flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (d_bwt)
+            TC_CUDA(cudaMemcpyAsync(ctx->h_scal + 8, d_primary, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (hU[0] <= (uint32_t)BS_CAP) {
-            TC_TRY(tc_scan_exclusive_u32(ctx, cnt, cnt, nbk, (uint32_t *)nullptr));
-            TC_LAUNCH(ctx, msd_scatter_kernel, gridN, 256, 0, pw, b, kb, bshift, N, cnt, d_sa);
-            const size_t bs_smem = sizeof(BsWarp) * BS_WARPS;
-            TC_CUDA(cudaFuncSetAttribute(msd_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bs_smem));
-            unsigned long long *d_next;
-            TC_TRY(ws_alloc(ctx, 1, &d_next));
-            TC_CUDA(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), ctx->stream));
-            unsigned sgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(nbk, BS_WARPS * 32), (uint64_t)ctx->sm_count * 3);
-            TC_CUDA(cudaMemsetAsync(d_U, 0, sizeof(uint32_t), ctx->stream));
-            // key bits needed below the prefix to split a bucket into singletons, judged by the symbol
-            // entropy per key bit: one counting round of 8 bits or two
-            double ebit = (entropy > 0.05 ? entropy : 0.05) / (double)b;
-            int nrounds = (log2((double)(hU[0] > 1 ? hU[0] : 2)) / ebit > 10.0) ? 2 : 1;
-            TC_LAUNCH(ctx, msd_bucket_sort_kernel, sgrid, BS_WARPS * 32, bs_smem, cnt, nbk, bshift, nrounds, pw, b, kb,
-                      d_sa, d_U, d_next);
-            TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            TC_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (hU[0] == 0) { // every suffix is already distinguished by its key: done
+        if (hU[FL_OVERFLOW] == 0) {
+            sorted = true;
+            if (hU[FL_TIES] == 0) { // every suffix is already distinguished by its key: done
+                if (bwt_done && d_bwt) {
+                    *bwt_done = true;
+                    if (primary) *primary = ctx->h_scal[8];
+                }
                 tc_ws_release(ctx, mk);
                 return TC_OK;
             }
             TC_TRY(ws_alloc(ctx, N, &keys));
             TC_LAUNCH(ctx, sa_gather_keys_kernel, gridN, 256, 0, pw, b, kb, d_sa, N, keys);
-            sorted = true;
         }
     }
     if (!sorted) { // LSD path
