@@ -148,7 +148,7 @@ __device__ __forceinline__ unsigned match_bits(uint32_t label, bool valid) {
     for (int b = 0; b < BITS; b++) {
         bool bit = (label >> b) & 1;
         unsigned m = __ballot_sync(TC_FULL, bit);
-        peers &= bit ? m : ~m;
+        peers &= m ^ (bit ? 0u : 0xffffffffu); // one select + one 3-input logic op per bit
     }
     return peers;
 }

@@ -388,6 +388,184 @@ __global__ void __launch_bounds__(32)
     }
 }
 
+// ---- encode, small alphabets (sigma <= 8: ACGT(N) + sentinel) -------------------------------------
+// The whole list fits one register: nibble j = rank at list position j.  A thread replays a chunk
+// of 64 symbols with ~14 integer instructions per symbol (find the nibble, rotate the ones below
+// it), so the pass is bound by HBM, not by issue.  Chunk summaries are recency lists (the distinct
+// ranks of the chunk, most recent first) + the set of ranks seen;  later . earlier  =  later's list
+// followed by earlier's entries that later has not seen -- associative, so incoming lists come from
+// an exclusive scan: inside the CTA by shuffles and shared memory (K1), over CTAs by one CTA (K2).
+constexpr int SM_L = 64;            // symbols per thread
+constexpr int SM_T = 256;           // threads per CTA
+constexpr int SM_TILE = SM_L * SM_T;
+struct Summ {
+    uint32_t list, mask;
+};
+__device__ __forceinline__ uint32_t nib_mtf(uint32_t &L, uint32_t s) {
+    uint32_t x = L ^ (s * 0x11111111u);
+    uint32_t t = (x - 0x11111111u) & ~x & 0x88888888u; // top bit of every zero nibble (lowest one exact)
+    uint32_t p4 = (uint32_t)__ffs((int)t) - 4u;        // bit offset of the nibble holding s
+    uint32_t low = (1u << p4) - 1u;
+    L = (L & ~((low << 4) | 0xFu)) | ((L & low) << 4) | s;
+    return p4 >> 2;
+}
+__device__ __forceinline__ Summ summ_compose(Summ earlier, Summ later) {
+    uint32_t pos = 4u * (uint32_t)__popc(later.mask);
+    uint32_t out = pos >= 32 ? later.list : (later.list & ((1u << pos) - 1u));
+    const uint32_t ke = (uint32_t)__popc(earlier.mask);
+    for (uint32_t j = 0; j < ke; j++) {
+        uint32_t s = (earlier.list >> (4 * j)) & 15u;
+        if (!((later.mask >> s) & 1u)) {
+            out |= s << pos;
+            pos += 4;
+        }
+    }
+    return Summ{out, earlier.mask | later.mask};
+}
+__device__ __forceinline__ Summ summ_shfl_up(Summ v, int d) {
+    return Summ{__shfl_up_sync(TC_FULL, v.list, d), __shfl_up_sync(TC_FULL, v.mask, d)};
+}
+
+template <class Src>
+__device__ __forceinline__ void sm_load_ranks(const Src &src, const uint8_t *s_rank, uint64_t base, uint64_t N,
+                                              int q, uint32_t *r /*16*/) {
+    int c[16];
+    uint64_t b0 = base + (uint64_t)q * 16;
+    if (b0 + 16 <= N && src.can_vec(b0)) {
+        src.load_vec(b0, c);
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = s_rank[c[k]];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = b0 + k < N ? s_rank[src.at(b0 + k)] : 0xffu;
+    }
+}
+
+// K1: chunk summaries, exclusive prefix inside the CTA -> part[chunk], CTA total -> tot[cta]
+template <class Src>
+__global__ void __launch_bounds__(SM_T)
+    mtfs_summary_kernel(Src src, Lut lut, uint64_t N, Summ *__restrict__ part, Summ *__restrict__ tot) {
+    __shared__ uint8_t s_rank[SIGMAX + 7];
+    __shared__ Summ wsum[SM_T / 32];
+    for (int j = threadIdx.x; j < SIGMAX; j += SM_T) s_rank[j] = (uint8_t)lut.rank[j];
+    __syncthreads();
+    const uint64_t chunk = (uint64_t)blockIdx.x * SM_T + threadIdx.x;
+    const uint64_t base = chunk * SM_L;
+    // recency list of the chunk = ranks in the order they are first met walking backwards
+    uint32_t L = 0, mask = 0, pos = 0;
+    if (base < N) {
+#pragma unroll
+        for (int q = SM_L / 16 - 1; q >= 0; q--) {
+            uint32_t r[16];
+            sm_load_ranks(src, s_rank, base, N, q, r);
+#pragma unroll
+            for (int k = 15; k >= 0; k--) {
+                if (r[k] < 8u && !((mask >> r[k]) & 1u)) {
+                    mask |= 1u << r[k];
+                    L |= r[k] << pos;
+                    pos += 4;
+                }
+            }
+        }
+    }
+    // inclusive scan over the warp, then over the CTA's warps
+    Summ v{L, mask};
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Summ o = summ_shfl_up(v, d);
+        if (lane >= (unsigned)d) v = summ_compose(o, v);
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane == 31) wsum[w] = v;
+    Summ ex = summ_shfl_up(v, 1);
+    if (lane == 0) ex = Summ{0, 0};
+    __syncthreads();
+    Summ pre{0, 0};
+    for (int ww = 0; ww < w; ww++) pre = summ_compose(pre, wsum[ww]);
+    if (base < N) part[chunk] = summ_compose(pre, ex);
+    if (threadIdx.x == SM_T - 1) tot[blockIdx.x] = summ_compose(pre, v);
+}
+
+// K2: one CTA; full list at the start of every CTA tile (seed = identity = sorted alphabet) and
+// the final list of the whole input
+__global__ void __launch_bounds__(1024)
+    mtfs_top_kernel(const Summ *__restrict__ tot, uint64_t ntiles, uint32_t sigma, uint32_t *__restrict__ start_list,
+                    uint16_t *__restrict__ final_list) {
+    __shared__ Summ wsum[32];
+    __shared__ Summ carry_s;
+    const unsigned lane = lane_id();
+    const int w = threadIdx.x >> 5;
+    const uint32_t full = sigma >= 32 ? 0xffffffffu : ((1u << sigma) - 1u);
+    Summ carry{0x76543210u, full};
+    for (uint64_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        uint64_t t = b0 + threadIdx.x;
+        Summ v = t < ntiles ? tot[t] : Summ{0, 0};
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Summ o = summ_shfl_up(v, d);
+            if (lane >= (unsigned)d) v = summ_compose(o, v);
+        }
+        if (lane == 31) wsum[w] = v;
+        Summ ex = summ_shfl_up(v, 1);
+        if (lane == 0) ex = Summ{0, 0};
+        __syncthreads();
+        if (w == 0) { // exclusive scan of the 32 warp totals, seeded with the carry
+            Summ x = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                Summ o = summ_shfl_up(x, d);
+                if (lane >= (unsigned)d) x = summ_compose(o, x);
+            }
+            Summ xe = summ_shfl_up(x, 1);
+            if (lane == 0) xe = Summ{0, 0};
+            wsum[lane] = summ_compose(carry, xe);
+            if (lane == 31) carry_s = summ_compose(carry, x);
+        }
+        __syncthreads();
+        if (t < ntiles) start_list[t] = summ_compose(wsum[w], ex).list;
+        carry = carry_s;
+        __syncthreads();
+    }
+    if (threadIdx.x < sigma) final_list[threadIdx.x] = (uint16_t)((carry.list >> (4 * threadIdx.x)) & 15u);
+}
+
+// K3: replay every chunk from its incoming list
+template <class Src>
+__global__ void __launch_bounds__(SM_T)
+    mtfs_replay_kernel(Src src, Lut lut, uint64_t N, const Summ *__restrict__ part,
+                       const uint32_t *__restrict__ start_list, uint32_t sigma, uint16_t *__restrict__ idx_out) {
+    __shared__ uint8_t s_rank[SIGMAX + 7];
+    for (int j = threadIdx.x; j < SIGMAX; j += SM_T) s_rank[j] = (uint8_t)lut.rank[j];
+    __syncthreads();
+    const uint64_t chunk = (uint64_t)blockIdx.x * SM_T + threadIdx.x;
+    const uint64_t base = chunk * SM_L;
+    if (base >= N) return;
+    const uint32_t full = (1u << sigma) - 1u;
+    uint32_t L = summ_compose(Summ{start_list[blockIdx.x], full}, part[chunk]).list;
+#pragma unroll
+    for (int q = 0; q < SM_L / 16; q++) {
+        uint32_t r[16];
+        sm_load_ranks(src, s_rank, base, N, q, r);
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint32_t x = r[k] < 8u ? nib_mtf(L, r[k]) : 0u;
+            o[k >> 1] = (k & 1) ? (o[k >> 1] | (x << 16)) : x;
+        }
+        const uint64_t b0 = base + (uint64_t)q * 16;
+        if (b0 + 16 <= N && (reinterpret_cast<uintptr_t>(idx_out + b0) & 15) == 0) {
+            uint4 *dst = reinterpret_cast<uint4 *>(idx_out + b0);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (b0 + k < N) idx_out[b0 + k] = (uint16_t)((o[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        }
+    }
+}
+
 // ---- decode ----------------------------------------------------------------------------------
 // D1: permutation each chunk applies to list positions (replay on the identity list).
 __global__ void mtfd_perm_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t L, uint64_t nchunks,
@@ -517,6 +695,28 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         } else {
             lut.rank[c] = 0;
         }
+    }
+    if (sigma <= 8) { // the list fits one register
+        const uint64_t nchunks = ceil_div_u64(N, SM_L), ntiles = ceil_div_u64(nchunks, SM_T);
+        Summ *part, *tot;
+        uint32_t *start_list;
+        uint16_t *d_final;
+        TC_TRY(ws_alloc(ctx, ntiles * SM_T, &part));
+        TC_TRY(ws_alloc(ctx, ntiles, &tot));
+        TC_TRY(ws_alloc(ctx, ntiles, &start_list));
+        TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+        ctx->prof_bytes_next = N * sizeof(*src.p);
+        TC_LAUNCH(ctx, (mtfs_summary_kernel<Src>), (unsigned)ntiles, SM_T, 0, src, lut, N, part, tot);
+        TC_LAUNCH(ctx, mtfs_top_kernel, 1, 1024, 0, tot, ntiles, sigma, start_list, d_final);
+        ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
+        TC_LAUNCH(ctx, (mtfs_replay_kernel<Src>), (unsigned)ntiles, SM_T, 0, src, lut, N, part, start_list, sigma, d_idx);
+        uint16_t *h_final = (uint16_t *)ctx->h_scal;
+        TC_CUDA(cudaMemcpyAsync(h_final, d_final, sigma * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
+        *sigma_out = sigma;
+        tc_ws_release(ctx, mk);
+        return TC_OK;
     }
     const uint32_t VS = (sigma + 31) / 32 * 32;
     // chunk length: a multiple of 32, enough chunks to fill the machine with warps

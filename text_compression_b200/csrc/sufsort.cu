@@ -100,8 +100,8 @@ struct SymProb {
     float p[258]; // p[code], code 0 = past the end
 };
 
-// lut[e] = cum16 << 16 | freq16 over all g-grams e in numeric (= lexicographic) order
-__global__ void __launch_bounds__(1024) uk_lut_kernel(SymProb sp, int sigma, int b, int g, uint32_t *__restrict__ lut) {
+// lut[e] = {cum16 << 16, freq16 << 16} over all g-grams e in numeric (= lexicographic) order
+__global__ void __launch_bounds__(1024) uk_lut_kernel(SymProb sp, int sigma, int b, int g, uint2 *__restrict__ lut) {
     __shared__ uint32_t sh[1024 / 32 + 1];
     const uint32_t E = 1u << (g * b);
     float nvalid = 1.f;
@@ -129,22 +129,41 @@ __global__ void __launch_bounds__(1024) uk_lut_kernel(SymProb sp, int sigma, int
             }
             if (cum + f > 65536u) f = 65536u - cum;
             if (f > 65535u) f = 65535u;
-            lut[e] = (cum << 16) | f;
+            lut[e] = make_uint2(cum << 16, f << 16);
         }
         carry += tot;
     }
 }
 
-__device__ __forceinline__ uint32_t ukey_of(uint64_t key, int kb, int gb, int G, const uint32_t *__restrict__ lut) {
+// G lookups of gb key bits each, from the top of the (right-aligned, kb-bit) key; G = 0: runtime Gr
+template <int G>
+__device__ __forceinline__ uint32_t ukey_of(uint64_t key, int kb, int gb, int Gr, const uint2 *lut /*shared*/) {
     uint32_t x = 0, r = 0xffffffffu;
     int sh = kb - gb;
     const uint32_t m = (1u << gb) - 1;
-    for (int j = 0; j < G; j++, sh -= gb) {
-        uint32_t e = __ldg(&lut[(uint32_t)(key >> sh) & m]);
-        x += __umulhi(r, e & 0xffff0000u);
-        r = __umulhi(r, e << 16);
+    if (G > 0) {
+#pragma unroll
+        for (int j = 0; j < G; j++, sh -= gb) {
+            uint2 e = lut[(uint32_t)(key >> sh) & m];
+            x += __umulhi(r, e.x);
+            r = __umulhi(r, e.y);
+        }
+    } else {
+        for (int j = 0; j < Gr; j++, sh -= gb) {
+            uint2 e = lut[(uint32_t)(key >> sh) & m];
+            x += __umulhi(r, e.x);
+            r = __umulhi(r, e.y);
+        }
     }
     return x;
+}
+// extract_key for texts whose bit offsets fit 32 bits
+__device__ __forceinline__ uint64_t extract_key32(const uint64_t *__restrict__ pw, uint32_t b, int kb, uint32_t i) {
+    const uint32_t o = i * b;
+    const uint64_t hi = pw[o >> 6], lo = pw[(o >> 6) + 1];
+    const int sh = (int)(o & 63u);
+    uint64_t v = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+    return v >> (64 - kb);
 }
 
 // bytes of a uint4 summed (each field of the result holds at most 16 * 255)
@@ -178,25 +197,29 @@ __device__ __forceinline__ uint32_t pc_total(const uint8_t *wc, int q, unsigned 
 }
 
 // K_A: ukey of every suffix 0..n-1 + histogram of the level-1 digit
+constexpr int UK_LUT_MAX = 512; // g-gram table entries (gb <= 9 bits), staged in shared memory
+template <int G>
 __global__ void __launch_bounds__(PC_T)
-    uk_keys_kernel(const uint64_t *__restrict__ pw, int b, int kb, int gb, int G, const uint32_t *__restrict__ lut,
-                   uint64_t n, int shift1, uint32_t *__restrict__ ukey, uint32_t *__restrict__ hist1) {
+    uk_keys_kernel(const uint64_t *__restrict__ pw, int b, int kb, int gb, int Gr, const uint2 *__restrict__ lut,
+                   uint32_t n, int shift1, uint32_t *__restrict__ ukey, uint32_t *__restrict__ hist1) {
     extern __shared__ __align__(16) uint8_t pc_cnt[];
     __shared__ uint16_t wtot[PC_WARPS][256];
+    __shared__ uint2 s_lut[UK_LUT_MAX];
     const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
+    for (int j = threadIdx.x; j < (1 << gb); j += PC_T) s_lut[j] = lut[j];
     uint8_t *wc = pc_cnt + (size_t)w * 8192;
     pc_zero(wc, lane);
-    __syncwarp();
-    const uint64_t tbase = (uint64_t)blockIdx.x * PC_TILE + (uint64_t)w * PC_WCHUNK;
+    __syncthreads();
+    const uint32_t tbase = blockIdx.x * PC_TILE + w * PC_WCHUNK;
+    uint8_t *mine = wc + lane;
 #pragma unroll 4
     for (int r = 0; r < PC_ITEMS; r++) {
-        uint64_t i = tbase + (uint64_t)r * 32 + lane;
+        uint32_t i = tbase + r * 32 + lane;
         if (i < n) {
-            uint32_t u = ukey_of(extract_key(pw, b, kb, i), kb, gb, G, lut);
+            uint32_t u = ukey_of<G>(extract_key32(pw, (uint32_t)b, kb, i), kb, gb, Gr, s_lut);
             ukey[i] = u;
-            uint32_t d = shift1 < 32 ? u >> shift1 : 0u;
-            wc[d * 32 + lane]++;
+            mine[(u >> shift1) * 32]++;
         }
     }
     __syncwarp();
@@ -756,7 +779,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         const uint32_t nbk = 1u << PB;
         const int packprev = (d_bwt && n <= (1ull << 24)) ? 1 : 0;
         // lookups of g symbols each; enough of them to spend the 32 bits of ukey
-        int gs = 12 / b;
+        int gs = 9 / b;
         if (gs < 1) gs = 1;
         if (gs > k) gs = k;
         const int gb = gs * b;
@@ -768,7 +791,8 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         sp.p[0] = 1.0f / (float)N;
         for (int c = 0; c < 256; c++)
             if (hist[c]) sp.p[lut.code[c]] = (float)((double)hist[c] / (double)N);
-        uint32_t *uk_lut, *ukey, *hist1, *hist2, *segstart, *cursor1, *tilebase, *chunkbase, *starts2, *cursor2, *flags;
+        uint2 *uk_lut;
+        uint32_t *ukey, *hist1, *hist2, *segstart, *cursor1, *tilebase, *chunkbase, *starts2, *cursor2, *flags;
         uint2 *recA, *recB = nullptr;
         uint64_t *d_primary = nullptr;
         if (d_bwt) TC_TRY(ws_alloc(ctx, 1, &d_primary));
@@ -786,14 +810,17 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         TC_TRY(ws_alloc(ctx, n, &recA));
         if (B2) TC_TRY(ws_alloc(ctx, n, &recB));
         TC_CUDA(cudaMemsetAsync(hist1, 0, (256 + (size_t)nbk + 8) * sizeof(uint32_t), ctx->stream));
-        TC_CUDA(cudaFuncSetAttribute(uk_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+        void (*kkeys)(const uint64_t *, int, int, int, int, const uint2 *, uint32_t, int, uint32_t *, uint32_t *) =
+            G == 3 ? uk_keys_kernel<3> : G == 4 ? uk_keys_kernel<4> : G == 5 ? uk_keys_kernel<5>
+            : G == 6 ? uk_keys_kernel<6> : uk_keys_kernel<0>;
+        TC_CUDA(cudaFuncSetAttribute(kkeys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
         TC_CUDA(cudaFuncSetAttribute(seg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
         TC_CUDA(cudaFuncSetAttribute(part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
         TC_CUDA(cudaFuncSetAttribute(part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
         TC_LAUNCH(ctx, uk_lut_kernel, 1, 1024, 0, sp, sigma, b, gs, uk_lut);
         ctx->prof_bytes_next = n + 4 * n;
-        TC_LAUNCH(ctx, uk_keys_kernel, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut, n,
-                  32 - B1, ukey, hist1);
+        TC_LAUNCH(ctx, kkeys, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut, (uint32_t)n,
+                  B1 ? 32 - B1 : 31, ukey, hist1);
         TC_LAUNCH(ctx, seg_tables_kernel, 1, 256, 0, hist1, nb1, segstart, cursor1, tilebase, chunkbase);
         ctx->prof_bytes_next = 4 * n + (packprev ? n : 0) + 8 * n;
         TC_LAUNCH(ctx, part_kernel<true>, (unsigned)ceil_div_u64(n, PT_TILE), PT_T, sizeof(PtSmem), ukey, d_text, packprev,
