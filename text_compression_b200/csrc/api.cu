@@ -266,7 +266,11 @@ int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, 
     if (!with_mtf) return rle_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_count, d_rsym, cap, &info->R);
     uint16_t *d_idx;
     TC_TRY(ws_alloc(ctx, N, &d_idx));
-    TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma));
+    // alphabet of the BWT = the text's bytes (histogram kept by the suffix sort) + the sentinel
+    uint8_t present[257];
+    present[0] = 1;
+    for (int c = 0; c < 256; c++) present[c + 1] = ctx->text_hist[c] != 0;
+    TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma, present));
     return rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R);
 }
 

@@ -30,6 +30,7 @@ struct tc_ctx {
     // pinned scalars for small device->host results
     uint64_t *h_scal = nullptr; // 1024 x u64, pinned
     uint64_t launches = 0;
+    uint32_t text_hist[256] = {0}; // byte histogram of the last text handed to the suffix sort
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     char err[512] = {0};
     // optional per-kernel timing (tc_ctx_profile): one event pair per launch
@@ -67,16 +68,18 @@ struct tc_ctx {
         int rc_ = (call);          \
         if (rc_ != TC_OK) return rc_; \
     } while (0)
-// kernel launch + bookkeeping
-#define TC_LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+// kernel launch + bookkeeping (TC_LAUNCH_AS: the profile name when `kernel` is a pointer)
+#define TC_LAUNCH_AS(ctx, name, kernel, grid, block, smem, ...)               \
     do {                                                                      \
-        if ((ctx)->prof_on) (ctx)->prof_begin(#kernel);                       \
+        if ((ctx)->prof_on) (ctx)->prof_begin(name);                          \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);      \
         if ((ctx)->prof_on) (ctx)->prof_end();                                \
         (ctx)->launches++;                                                    \
         cudaError_t e_ = cudaPeekAtLastError();                               \
-        if (e_ != cudaSuccess) return (ctx)->fail(e_, #kernel, __LINE__);     \
+        if (e_ != cudaSuccess) return (ctx)->fail(e_, name, __LINE__);        \
     } while (0)
+#define TC_LAUNCH(ctx, kernel, grid, block, smem, ...) \
+    TC_LAUNCH_AS(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 // ---- arena -------------------------------------------------------------------
 // ws_reset(): called at the start of a top-level op.  If the previous op spilled

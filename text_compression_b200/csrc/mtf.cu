@@ -136,14 +136,17 @@ __global__ void __launch_bounds__(ENC_WARPS * 32)
             uint64_t pos = b0 + q * 32 + lane;
             c[q] = pos < end ? (int)s_rank[src.at(pos)] : -1;
         }
+        // rows ascend, so a later row simply overwrites; inside a row the largest position must
+        // win: plain stores, re-tried by the lanes that read back something smaller
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-            uint64_t pos = b0 + q * 32 + lane;
-            bool valid = c[q] >= 0;
-            unsigned peers = match_bits<9>((uint32_t)c[q], valid);
-            bool is_last = valid && (peers & ~((2u << lane) - 1)) == 0; // no later lane holds the same rank
-            if (is_last) lo[w][c[q]] = (uint32_t)pos + 1;
-            __syncwarp();
+            const uint32_t v = (uint32_t)(b0 + q * 32 + lane) + 1;
+            bool again = c[q] >= 0;
+            do {
+                if (again) lo[w][c[q]] = v;
+                __syncwarp();
+                again = again && lo[w][c[q]] < v;
+            } while (__any_sync(TC_FULL, again));
         }
     }
     for (int j = lane; j < (int)VS; j += 32) lastocc[k * VS + j] = lo[w][j];
@@ -670,21 +673,30 @@ uint32_t pick_chunk_len(tc_ctx *ctx, uint64_t N, uint32_t lo, uint32_t hi) {
     return (uint32_t)L;
 }
 
+// present_hint (257 flags, code = symbol + 1, 0 = Nothing): the alphabet when the caller already
+// knows it (the composed helpers do: a BWT has the symbols of its text plus the sentinel)
 template <class Src>
-int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *final_list, uint32_t *sigma_out) {
+int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *final_list, uint32_t *sigma_out,
+                    const uint8_t *present_hint = nullptr) {
     *sigma_out = 0;
     if (N == 0) return TC_OK;
     if (N >= 0x7fffffffull) return TC_E_TOOBIG; // recency keys are 32-bit distances (see list_positions)
     WsMark mk = tc_ws_mark(ctx);
     // alphabet = nubSeq' (sorted, Nothing first)
-    uint32_t *d_present;
-    TC_TRY(ws_alloc(ctx, SIGMAX, &d_present));
-    TC_CUDA(cudaMemsetAsync(d_present, 0, SIGMAX * sizeof(uint32_t), ctx->stream));
-    unsigned pgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256 * 16), (uint64_t)ctx->sm_count * 8);
-    TC_LAUNCH(ctx, (mtf_presence_kernel<Src>), pgrid, 256, 0, src, N, d_present);
-    uint32_t *h_present = (uint32_t *)ctx->h_scal;
-    TC_CUDA(cudaMemcpyAsync(h_present, d_present, SIGMAX * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint32_t h_present_buf[SIGMAX];
+    if (present_hint) {
+        for (int c = 0; c < SIGMAX; c++) h_present_buf[c] = present_hint[c];
+    } else {
+        uint32_t *d_present;
+        TC_TRY(ws_alloc(ctx, SIGMAX, &d_present));
+        TC_CUDA(cudaMemsetAsync(d_present, 0, SIGMAX * sizeof(uint32_t), ctx->stream));
+        unsigned pgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256 * 16), (uint64_t)ctx->sm_count * 8);
+        TC_LAUNCH(ctx, (mtf_presence_kernel<Src>), pgrid, 256, 0, src, N, d_present);
+        TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_present, SIGMAX * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(h_present_buf, ctx->h_scal, SIGMAX * sizeof(uint32_t));
+    }
+    const uint32_t *h_present = h_present_buf;
     Lut lut;
     int16_t alpha[SIGMAX];
     uint32_t sigma = 0;
@@ -736,6 +748,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
     TC_LAUNCH(ctx, (mtf2_lastocc_kernel<Src>), cgrid, ENC_WARPS * 32, 0, src, lut, N, L, nchunks, VS, lastocc);
     TC_LAUNCH(ctx, mtf2_scan_tiles_kernel, (unsigned)ntiles, VSMAX, 0, lastocc, nchunks, G, VS, tiletot);
     TC_LAUNCH(ctx, mtf2_scan_top_kernel, 1, VSMAX, 0, tiletot, ntiles, VS, finalocc);
+    ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
     TC_LAUNCH(ctx, (mtf2_replay_kernel<Src>), cgrid, ENC_WARPS * 32, 0, src, lut, N, L, nchunks, G, sigma, VS, lastocc,
               tiletot, d_idx);
     TC_LAUNCH(ctx, mtf2_final_kernel, 1, 32, 0, finalocc, N, sigma, VS, d_final);
@@ -750,9 +763,9 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
 } // namespace
 
 int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
-                           int16_t *final_list, uint32_t *sigma) {
+                           int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint) {
     if (N && primary >= N) primary = ~0ull;
-    return mtf_encode_impl(ctx, SrcU8{d_bwt, primary}, N, d_idx, final_list, sigma);
+    return mtf_encode_impl(ctx, SrcU8{d_bwt, primary}, N, d_idx, final_list, sigma, present_hint);
 }
 int mtf_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint16_t *d_idx, int16_t *final_list,
                                uint32_t *sigma) {

@@ -744,6 +744,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
     WsMark mk = tc_ws_mark(ctx);
     uint32_t hist[256];
     TC_TRY(tc_byte_hist_dev(ctx, d_text, n, hist));
+    memcpy(ctx->text_hist, hist, sizeof hist);
     Code256 lut;
     int sigma = 0;
     double entropy = 0;
@@ -819,7 +820,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         TC_CUDA(cudaFuncSetAttribute(part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
         TC_LAUNCH(ctx, uk_lut_kernel, 1, 1024, 0, sp, sigma, b, gs, uk_lut);
         ctx->prof_bytes_next = n + 4 * n;
-        TC_LAUNCH(ctx, kkeys, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut, (uint32_t)n,
+        TC_LAUNCH_AS(ctx, "uk_keys_kernel", kkeys, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut, (uint32_t)n,
                   B1 ? 32 - B1 : 31, ukey, hist1);
         TC_LAUNCH(ctx, seg_tables_kernel, 1, 256, 0, hist1, nb1, segstart, cursor1, tilebase, chunkbase);
         ctx->prof_bytes_next = 4 * n + (packprev ? n : 0) + 8 * n;

@@ -26,11 +26,18 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, cap
 cubin = glob.glob(tmp + "/*.cubin")[0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", "-c", cubin], capture_output=True, text=True).stdout
 short = re.sub(r"[^A-Za-z0-9_]", "", b["name"].split("(")[0].split("::")[-1].split("<")[0])
-infn, line, agg, ins = False, None, collections.Counter(), collections.Counter()
+# several template instances may share the name: take the section whose size matches the report
+secs, cur = {}, None
 for l in dis.splitlines():
     if l.startswith("\t.section\t.text."):
-        infn = short in l
-    if not infn: continue
+        cur = l if short in l else None
+        if cur: secs[cur] = []
+        continue
+    if cur is not None: secs[cur].append(l)
+def ninstr(ls): return sum(1 for l in ls if re.match(r"\s*/\*([0-9a-f]{4,})\*/", l))
+best = min(secs, key=lambda k: abs(ninstr(secs[k]) - len(per_off)))
+line, agg, ins = None, collections.Counter(), collections.Counter()
+for l in secs[best]:
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: line = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
