@@ -216,6 +216,53 @@ def test_bwt_decode_malformed(ctx, orc):
     assert n_ok > 0
 
 
+# ---------------------------------------------------------------- suffix-sort paths
+def _sort_path_cases():
+    rng = np.random.default_rng(23)
+    a = gen_acgt(5, 6000)
+    yield "repeat_block", np.concatenate([a, gen_acgt(6, 3000), a, a[:2500]])          # ties far beyond the key
+    yield "low_entropy", np.where(rng.random(40000) < 0.97, 65, rng.integers(66, 70, 40000)).astype(np.uint8)
+    yield "two_symbols", rng.integers(0, 2, 30000).astype(np.uint8) + 97
+    yield "runs", np.repeat(gen_acgt(7, 3000), rng.integers(1, 30, 3000))
+    yield "bytes_8191", gen_bytes(1, 8191)
+    yield "bytes_4096", gen_bytes(2, 4096)
+    yield "acgtn_300k", gen_acgtn(3, 300_000)
+    yield "ascii_131k", gen_ascii(4, 131_072)
+    yield "zero_bytes", np.where(rng.random(50000) < 0.5, 0, rng.integers(0, 4, 50000)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("name,text", list(_sort_path_cases()), ids=[c[0] for c in _sort_path_cases()])
+def test_suffix_sort_msd_and_fallback(ctx, orc, name, text, monkeypatch):
+    """The same inputs through the MSD path (default) and the LSD + prefix-doubling path
+    (TC_B200_NO_MSD=1, read at context creation): both must equal the oracle's suffix array."""
+    from text_compression_b200 import _lib
+    from text_compression_b200.bwt import bwt_u8
+    want_bwt, want_sa = orc.bwt_encode(text, want_sa=True)
+    bwt, primary, sa = bwt_u8(text, want_sa=True, ctx=ctx)
+    assert np.array_equal(sa, want_sa), name
+    assert primary == int(np.nonzero(want_bwt < 0)[0][0])
+    monkeypatch.setenv("TC_B200_NO_MSD", "1")
+    c2 = _lib.Context(0)
+    try:
+        bwt2, primary2, sa2 = bwt_u8(text, want_sa=True, ctx=c2)
+    finally:
+        c2.close()
+    assert np.array_equal(sa2, want_sa), name
+    assert primary2 == primary and np.array_equal(np.delete(bwt2, primary2), np.delete(bwt, primary))
+
+
+def test_block_over_16mib_roundtrip(ctx):
+    """n > 2^24: the record no longer has room for the preceding byte, so the last sort level
+    gathers the BWT symbols from the text instead."""
+    from text_compression_b200 import block
+    text = gen_acgtn(0xC5, (16 << 20) + 12345)
+    blk = block.compress_bwt_mtf_rle(text, ctx)
+    assert blk.N == text.size + 1 and int(blk.counts.sum()) == blk.N
+    assert block.decompress(blk, ctx) == text.tobytes()
+    blk2 = block.compress_bwt_rle(gen_acgtn(0xC6, 16 << 20), ctx)
+    assert block.decompress(blk2, ctx) == gen_acgtn(0xC6, 16 << 20).tobytes()
+
+
 # ---------------------------------------------------------------- reference's own tests, through the API
 def test_reference_hunit_vectors(ctx, golden):
     from text_compression_b200 import rle as R, mtf as M
