@@ -122,6 +122,16 @@ int tc_bwt_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *co
  * stream (the BWT+MTF+RLE composite of BASELINE.json). */
 int tc_bwt_mtf_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *count, int16_t *rsym, uint64_t cap,
                           tc_block_info *info);
+/* The same composite over a batch of independent blocks (BASELINE.json config 5: multi-block
+ * compression; the reference maps bytestringToBWTToMTFB over its blocks one by one,
+ * src/Data/MTF.hs:82-84).  Block b+1 is copied to the device and block b-1's runs are copied
+ * back while block b is being compressed (three streams, double buffers), so a stream of
+ * blocks runs at max(copy, compute) instead of their sum.  with_mtf = 0 gives
+ * bytestringToBWTToRLEB per block.  count[b] / rsym[b] hold cap[b] entries each; info[b] is
+ * filled per block; a block whose runs exceed cap[b] is reported as TC_E_CAP after the whole
+ * batch has been processed (info[b].R tells the size needed). */
+int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n, int with_mtf,
+                     uint32_t *const *count, int16_t *const *rsym, const uint64_t *cap, tc_block_info *info);
 /* inverses: runs -> (MTF indices ->) BWT -> text. */
 int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
                       uint64_t cap, uint64_t *n_out);

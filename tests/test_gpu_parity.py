@@ -360,6 +360,28 @@ def test_composites(ctx, orc, gen, n):
     assert block.decompress(b2, ctx) == text.tobytes()
 
 
+def test_compress_blocks_pipeline(ctx, orc):
+    """tc_blocks_encode (copies overlapped with compute) gives, block by block, exactly what the
+    single-block call gives -- ragged sizes, an empty block, both chains."""
+    from text_compression_b200 import block
+    texts = [gen_acgtn(1, 70001), gen_bytes(2, 4096), np.empty(0, np.uint8), gen_ascii(3, 33333), gen_acgt(4, 5),
+             gen_bytes(5, 200000), gen_acgtn(6, 1)]
+    for with_mtf in (True, False):
+        got = block.compress_blocks(texts, with_mtf, ctx)
+        assert len(got) == len(texts)
+        for t, g in zip(texts, got):
+            one = (block.compress_bwt_mtf_rle if with_mtf else block.compress_bwt_rle)(t, ctx)
+            assert (g.n, g.N, g.primary, g.sigma) == (one.n, one.N, one.primary, one.sigma)
+            assert g.final_list.tolist() == one.final_list.tolist()
+            assert np.array_equal(g.counts, one.counts) and np.array_equal(g.syms, one.syms)
+            if with_mtf or g.primary != g.N - 1:   # Q1: the reference's own round trip breaks there
+                assert block.decompress(g, ctx) == t.tobytes()
+    bwt = orc.bwt_encode(texts[0])
+    cnt, sym = orc.rle_encode(bwt)
+    g0 = block.compress_blocks(texts[:1], False, ctx, pinned=False)[0]
+    assert g0.counts.tolist() == cnt.tolist() and g0.syms.tolist() == sym.tolist()
+
+
 def test_q1_trailing_nothing_stream(ctx, orc):
     """Texts that are their own greatest suffix: the reference's RLE re-emits a stale pair (Q1)
     and its own round trip breaks; the GPU stream must equal the oracle's, not round-trip."""

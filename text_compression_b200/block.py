@@ -56,6 +56,37 @@ def compress_bwt_mtf_rle(text, ctx=None) -> CompressedBlock:
     return _compress("tc_bwt_mtf_rle_encode", text, ctx, True)
 
 
+def compress_blocks(texts, with_mtf: bool = True, ctx=None, pinned: bool = True) -> list:
+    """Multi-block compression (BASELINE.json config 5) through tc_blocks_encode: the copy of
+    block b+1 to the device and of block b-1's runs back overlap the compression of block b.
+    Returns one CompressedBlock per input, in input order."""
+    from ._lib import pinned_empty
+    ctx = ctx or default_context()
+    ts = [np.ascontiguousarray(t if isinstance(t, np.ndarray) else np.frombuffer(to_bytes(t), dtype=np.uint8),
+                               dtype=np.uint8) for t in texts]
+    nb = len(ts)
+    if nb == 0:
+        return []
+    alloc = pinned_empty if pinned else (lambda k, dt: np.empty(k, dtype=dt))
+    ns = (C.c_uint64 * nb)(*[t.size for t in ts])
+    caps = (C.c_uint64 * nb)(*[t.size + 3 for t in ts])
+    cnts = [alloc(t.size + 3, np.uint32) for t in ts]
+    syms = [alloc(t.size + 3, np.int16) for t in ts]
+    tp = (C.c_void_p * nb)(*[t.ctypes.data for t in ts])
+    cp = (C.c_void_p * nb)(*[c.ctypes.data for c in cnts])
+    sp = (C.c_void_p * nb)(*[s.ctypes.data for s in syms])
+    infos = (BlockInfo * nb)()
+    ctx.call("tc_blocks_encode", nb, tp, ns, 1 if with_mtf else 0, cp, sp, caps, infos)
+    out = []
+    for b in range(nb):
+        i = infos[b]
+        R = int(i.R)
+        fin = np.array(i.final_list[: i.sigma], dtype=np.int16)
+        out.append(CompressedBlock(ts[b].size, int(i.N), int(i.primary), int(i.sigma), fin, cnts[b][:R].copy(),
+                                   syms[b][:R].copy(), with_mtf))
+    return out
+
+
 def decompress(blk: CompressedBlock, ctx=None) -> bytes:
     ctx = ctx or default_context()
     if blk.R == 0:

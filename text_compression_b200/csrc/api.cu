@@ -315,6 +315,72 @@ extern "C" int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uin
     return compress_dev(ctx, d_text, n, true, d_count, d_rsym, cap, info);
 }
 
+// Pipelined batch: slot = b & 1.  H2D of block b+1 is issued before block b is compressed, the
+// D2H of block b right after it (compress_dev returns with the stream drained, so the host
+// knows R); compressing block b+2 into the same slot first waits for that D2H.
+extern "C" int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n,
+                                int with_mtf, uint32_t *const *count, int16_t *const *rsym, const uint64_t *cap,
+                                tc_block_info *info) {
+    TC_ENTER(ctx);
+    if (nblocks == 0) return TC_OK;
+    if (!text || !n || !count || !rsym || !cap || !info) return TC_E_ARG;
+    uint64_t nmax = 0;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+        nmax = n[b] > nmax ? n[b] : nmax;
+    }
+    if (!ctx->s_h2d) {
+        TC_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        TC_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+        TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp, cudaEventDisableTiming));
+    }
+    const uint64_t worst = nmax + 3;
+    uint8_t *d_text[2];
+    uint32_t *d_count[2];
+    int16_t *d_rsym[2];
+    for (int s = 0; s < 2; s++) {
+        TC_TRY(ws_alloc(ctx, nmax ? nmax : 1, &d_text[s]));
+        TC_TRY(ws_alloc(ctx, worst, &d_count[s]));
+        TC_TRY(ws_alloc(ctx, worst, &d_rsym[s]));
+    }
+    // everything queued earlier on the context's stream must be done before the copy streams touch the arena
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    bool d2h_pending[2] = {false, false};
+    int rc_all = TC_OK;
+    auto issue_h2d = [&](uint64_t b) -> int {
+        const int s = (int)(b & 1);
+        if (n[b]) TC_CUDA(cudaMemcpyAsync(d_text[s], text[b], n[b], cudaMemcpyHostToDevice, ctx->s_h2d));
+        TC_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d));
+        return TC_OK;
+    };
+    TC_TRY(issue_h2d(0));
+    for (uint64_t b = 0; b < nblocks; b++) {
+        const int s = (int)(b & 1);
+        if (b + 1 < nblocks) TC_TRY(issue_h2d(b + 1)); // its slot's text was consumed by block b-1 (host-synced)
+        TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
+        if (d2h_pending[s]) TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));
+        WsMark mk = tc_ws_mark(ctx);
+        int rc = compress_dev(ctx, d_text[s], n[b], with_mtf != 0, d_count[s], d_rsym[s], worst, &info[b]);
+        tc_ws_release(ctx, mk);
+        if (rc != TC_OK) return rc;
+        TC_CUDA(cudaStreamSynchronize(ctx->stream)); // a no-op when compress_dev already drained it
+        uint64_t m = info[b].R < cap[b] ? info[b].R : cap[b];
+        if (info[b].R > cap[b]) rc_all = TC_E_CAP;
+        if (m) {
+            TC_CUDA(cudaMemcpyAsync(count[b], d_count[s], m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+            TC_CUDA(cudaMemcpyAsync(rsym[b], d_rsym[s], m * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+        TC_CUDA(cudaEventRecord(ctx->ev_d2h[s], ctx->s_d2h));
+        d2h_pending[s] = true;
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+    return rc_all;
+}
+
 extern "C" int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
                                  uint64_t cap, uint64_t *n_out) {
     TC_ENTER(ctx);

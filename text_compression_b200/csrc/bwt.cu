@@ -158,7 +158,7 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
     unsigned grid = (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256), (uint64_t)ctx->sm_count * 16);
     TC_LAUNCH(ctx, (inv_keys_kernel<Src>), grid, 256, 0, src, N, k0, v0, d_hist);
     uint32_t *h = (uint32_t *)ctx->h_scal;
-    TC_CUDA(cudaMemcpyAsync(h, d_hist, 257 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, h, d_hist, 257 * sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h[0] == 0) { // no Nothing: empty result (src/Data/BWT/Internal.hs:174-175)
         tc_ws_release(ctx, mk);
@@ -199,8 +199,8 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
         std::swap(dA, dB);
     }
     TC_LAUNCH(ctx, inv_walk2_kernel, gridS, 128, 0, psi, S, K, nxtA, dA, cs, d_text, cap, N, d_err);
-    TC_CUDA(cudaMemcpyAsync(h, dA, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    TC_CUDA(cudaMemcpyAsync(h + 1, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, h, dA, sizeof(uint32_t)));
+    TC_TRY(tc_d2h_small(ctx, h + 1, d_err, sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t total = h[0];
     bool bad = h[1] != 0;
@@ -218,7 +218,7 @@ int tc_bwt_emit_dev(tc_ctx *ctx, const uint8_t *d_text, const uint32_t *d_sa, ui
     TC_TRY(ws_alloc(ctx, 1, &d_primary));
     TC_LAUNCH(ctx, bwt_emit_kernel, (unsigned)ceil_div_u64(N, 256), 256, 0, d_text, d_sa, N, d_bwt, d_primary,
               (uint32_t *)nullptr);
-    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_primary, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_primary, sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     *primary = ctx->h_scal[0];
     return TC_OK;
@@ -242,7 +242,7 @@ int bwt_encode_dev_impl(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint8_t 
     } else if (!done) {
         TC_LAUNCH(ctx, bwt_emit_kernel, (unsigned)ceil_div_u64(N, 256), 256, 0, d_text, d_sa, N, d_bwt, d_primary,
                   d_sa_1based);
-        TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_primary, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_primary, sizeof(uint64_t)));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         *primary = ctx->h_scal[0];
     }

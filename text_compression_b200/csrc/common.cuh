@@ -19,6 +19,9 @@ struct tc_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // copy streams + events of the batch entry point (created on first use)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_comp = nullptr;
     // Grow-only scratch arena: pointers handed out stay valid until the next ws_reset().
     struct Chunk {
         char *p;
@@ -102,6 +105,11 @@ WsMark tc_ws_mark(tc_ctx *ctx);
 void tc_ws_release(tc_ctx *ctx, WsMark m);
 
 static inline uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Small device -> host result (a few bytes into the context's pinned, device-mapped scalars):
+// written by a one-block kernel instead of a memcpy, so it never queues behind a bulk D2H copy
+// that another stream has on the copy engine (tc_blocks_encode overlaps those with compute).
+int tc_d2h_small(tc_ctx *ctx, void *h_pinned_dst, const void *d_src, size_t bytes);
 
 // ---- internal device-level entry points (all pointers are device pointers) ----
 // radix sort of (u64 key, u32 val) pairs by the bit ranges listed (LSD, 8 bits per pass).

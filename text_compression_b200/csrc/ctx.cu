@@ -71,6 +71,13 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &c : ctx->chunks) cudaFree(c.p);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    if (ctx->ev_comp) cudaEventDestroy(ctx->ev_comp);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -193,4 +200,15 @@ void tc_ws_release(tc_ctx *ctx, WsMark m) {
         ctx->cur_off = m.off;
         ctx->used_total = m.used;
     }
+}
+
+static __global__ void d2h_small_kernel(unsigned char *dst, const unsigned char *src, size_t bytes) {
+    for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+int tc_d2h_small(tc_ctx *ctx, void *h_pinned_dst, const void *d_src, size_t bytes) {
+    if (bytes == 0) return TC_OK;
+    d2h_small_kernel<<<1, 256, 0, ctx->stream>>>((unsigned char *)h_pinned_dst, (const unsigned char *)d_src, bytes);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return ctx->fail(e, "d2h_small_kernel", __LINE__);
+    return TC_OK;
 }

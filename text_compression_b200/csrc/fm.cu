@@ -494,7 +494,7 @@ static int fm_locate_dev_impl(tc_ctx *ctx, const tc_fm *fm, const uint8_t *d_pat
     TC_TRY(ws_alloc(ctx, q, &d_n));
     TC_TRY(fm_count_dev_impl(ctx, fm, d_pats, d_off, q, nullptr, d_s, d_n));
     TC_TRY(tc_scan_exclusive_u32_to_u64(ctx, d_n, d_hit_off, q, d_hit_off + q));
-    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_hit_off + q, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_hit_off + q, sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t H = ctx->h_scal[0];
     *total = H;

@@ -692,7 +692,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         TC_CUDA(cudaMemsetAsync(d_present, 0, SIGMAX * sizeof(uint32_t), ctx->stream));
         unsigned pgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256 * 16), (uint64_t)ctx->sm_count * 8);
         TC_LAUNCH(ctx, (mtf_presence_kernel<Src>), pgrid, 256, 0, src, N, d_present);
-        TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_present, SIGMAX * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_present, SIGMAX * sizeof(uint32_t)));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         memcpy(h_present_buf, ctx->h_scal, SIGMAX * sizeof(uint32_t));
     }
@@ -723,7 +723,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
         TC_LAUNCH(ctx, (mtfs_replay_kernel<Src>), (unsigned)ntiles, SM_T, 0, src, lut, N, part, start_list, sigma, d_idx);
         uint16_t *h_final = (uint16_t *)ctx->h_scal;
-        TC_CUDA(cudaMemcpyAsync(h_final, d_final, sigma * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
         *sigma_out = sigma;
@@ -753,7 +753,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
               tiletot, d_idx);
     TC_LAUNCH(ctx, mtf2_final_kernel, 1, 32, 0, finalocc, N, sigma, VS, d_final);
     uint16_t *h_final = (uint16_t *)ctx->h_scal;
-    TC_CUDA(cudaMemcpyAsync(h_final, d_final, sigma * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
     *sigma_out = sigma;
@@ -809,7 +809,7 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
     TC_LAUNCH(ctx, mtfd_top_chain_kernel, 1, 32, 0, tilesum, ntiles, sigma, l0, tileprefix);
     TC_LAUNCH(ctx, mtfd_replay_kernel, cgrid, T, smem, d_idx, N, L, nchunks, G, sigma, part, tileprefix, d_sym);
     uint32_t *h_err = (uint32_t *)ctx->h_scal;
-    TC_CUDA(cudaMemcpyAsync(h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, h_err, d_err, sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     tc_ws_release(ctx, mk);
     return h_err[0] ? TC_E_INDEX : TC_OK;

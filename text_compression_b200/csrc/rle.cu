@@ -255,7 +255,7 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
     // for the owner of position N-1, which is always in the last tile, so offsets stay exact.
     TC_LAUNCH(ctx, rle_tile_scan_kernel, 1, 1024, 0, tp, th, tj, toff, tiles);
     TC_LAUNCH(ctx, (rle_emit_kernel<In>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap, d_R);
-    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_R, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     *R = ctx->h_scal[0];
     tc_ws_release(ctx, mk);
@@ -328,7 +328,7 @@ int rle_decode_dev_impl(tc_ctx *ctx, const uint32_t *d_count, const int16_t *d_r
     TC_TRY(ws_alloc(ctx, 1, &d_total));
     TC_LAUNCH(ctx, rle_len_kernel, (unsigned)ceil_div_u64(R, 256), 256, 0, d_count, d_rsym, R, len);
     TC_TRY(tc_scan_exclusive_u32_to_u64(ctx, len, off, R, d_total));
-    TC_CUDA(cudaMemcpyAsync(ctx->h_scal, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_total, sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t total = ctx->h_scal[0];
     *N_out = total;

@@ -719,7 +719,7 @@ int tc_byte_hist_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *h
         TC_LAUNCH(ctx, byte_hist_kernel, grid, 256, 0, d_text, n, d_hist);
     }
     uint32_t *h = (uint32_t *)ctx->h_scal;
-    TC_CUDA(cudaMemcpyAsync(h, d_hist, 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, h, d_hist, 256 * sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(h_hist, h, 256 * sizeof(uint32_t));
     return TC_OK;
@@ -846,9 +846,9 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         ctx->prof_bytes_next = 8 * n + 4 * n + (d_bwt ? n : 0);
         TC_LAUNCH(ctx, final_sort_kernel, (unsigned)ceil_div_u64(nbk, FS_WARPS), FS_WARPS * 32, 0, recF, startsF, nbk,
                   32 - PB, pw, b, kb, k, n, packprev, d_text, d_sa, d_bwt, d_primary, flags);
-        TC_CUDA(cudaMemcpyAsync(hU, flags, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        TC_TRY(tc_d2h_small(ctx, hU, flags, 2 * sizeof(uint32_t)));
         if (d_bwt)
-            TC_CUDA(cudaMemcpyAsync(ctx->h_scal + 8, d_primary, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            TC_TRY(tc_d2h_small(ctx, ctx->h_scal + 8, d_primary, sizeof(uint64_t)));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (hU[FL_OVERFLOW] == 0) {
             sorted = true;
@@ -891,7 +891,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
     TC_TRY(tc_scan_inclusive_max_u32(ctx, g, g, N));
     TC_LAUNCH(ctx, sa_flags_kernel, gridN, 256, 0, g, N, ns);
     TC_TRY(tc_scan_exclusive_u32(ctx, ns, cpos, N, d_U));
-    TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    TC_TRY(tc_d2h_small(ctx, hU, d_U, sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t U = hU[0];
     if (U > 0) {
@@ -937,7 +937,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
             TC_LAUNCH(ctx, sa_update_kernel, gridU, 256, 0, g2, cjA, v2s, U, d_sa, isa, g, ns2);
             TC_TRY(tc_scan_exclusive_u32(ctx, ns2, cpos2, U, d_U));
             TC_LAUNCH(ctx, sa_compact_kernel, gridU, 256, 0, ns2, cpos2, (const uint32_t *)cjA, U, cjB);
-            TC_CUDA(cudaMemcpyAsync(hU, d_U, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            TC_TRY(tc_d2h_small(ctx, hU, d_U, sizeof(uint32_t)));
             TC_CUDA(cudaStreamSynchronize(ctx->stream));
             U = hU[0];
             std::swap(cjA, cjB);
