@@ -421,18 +421,87 @@ __global__ void __launch_bounds__(PT_T, 4)
 }
 
 // Final level: one warp sorts one bucket (<= FS_CAP records) by the low `rb` bits of ukey.
-// Elements are (field << 9 | local index) in one word, so an LSD round moves 4 bytes per
-// record; 8-bit rounds, stable ranking by match groups.  Records whose field ties with a
-// neighbour are ordered by their full keys (rare: about N^2 / 2^33 pairs).
+// Elements are (field << 9 | local index) in one 32-bit word, so a compare-exchange is a min and
+// a max: the bucket is sorted by a bitonic network held in registers (8 or 16 elements per
+// lane; partner in the same lane for small strides, one shuffle otherwise) -- no shared-memory
+// counters, no match groups, about 1/3 of the instructions of two 8-bit counting rounds.
+// Records whose field ties with a neighbour are ordered by their full keys (rare: about
+// N^2 / 2^33 pairs).
 constexpr int FS_WARPS = 8;
 constexpr int FS_CAP = 512;
-constexpr int FS_PER = FS_CAP / 32;
 struct FsWarp {
     uint32_t e[FS_CAP];
-    uint32_t v[FS_CAP];
-    uint16_t cnt[256];
 };
 enum { FL_TIES = 0, FL_OVERFLOW = 1 };
+
+// ascending sort of 32*PER words, element index = lane * PER + r.  "Flip" form of the bitonic
+// network: the first step of every merge pairs e with e ^ (k-1), the others e with e ^ j, and
+// every compare-exchange leaves the minimum at the lower index -- no direction flags.
+template <int PER>
+__device__ __forceinline__ void warp_bitonic(uint32_t (&v)[PER], unsigned lane) {
+#pragma unroll
+    for (int k = 2; k <= 32 * PER; k <<= 1) {
+        // flip step: partner = e ^ (k - 1)
+        if (k <= PER) {
+#pragma unroll
+            for (int r = 0; r < PER; r++) {
+                const int p = r ^ (k - 1);
+                if (p > r) {
+                    uint32_t a = min(v[r], v[p]), c = max(v[r], v[p]);
+                    v[r] = a;
+                    v[p] = c;
+                }
+            }
+        } else {
+            const int lx = k / PER - 1;                       // partner lane = lane ^ lx, partner r = PER-1-r
+            const bool lower = (lane & (k / PER / 2)) == 0;
+            uint32_t o[PER];
+#pragma unroll
+            for (int r = 0; r < PER; r++) o[r] = __shfl_xor_sync(TC_FULL, v[PER - 1 - r], lx);
+#pragma unroll
+            for (int r = 0; r < PER; r++) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            if (j >= PER) {
+                const int lx = j / PER;
+                const bool lower = (lane & lx) == 0;
+#pragma unroll
+                for (int r = 0; r < PER; r++) {
+                    uint32_t o = __shfl_xor_sync(TC_FULL, v[r], lx);
+                    v[r] = lower ? min(v[r], o) : max(v[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < PER; r++) {
+                    const int p = r ^ j;
+                    if (p > r) {
+                        uint32_t a = min(v[r], v[p]), c = max(v[r], v[p]);
+                        v[r] = a;
+                        v[p] = c;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// load the bucket (coalesced), sort it, leave the sorted words in we[0..M)
+template <int PER>
+__device__ __forceinline__ void fs_sort_bucket(const uint2 *__restrict__ rec, uint32_t M, int fsh, uint32_t fmask,
+                                               uint32_t *we, unsigned lane) {
+    uint32_t v[PER];
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+        uint32_t j = lane + 32 * r; // any assignment of records to registers will do
+        v[r] = j < M ? ((((rec[j].x >> fsh) & fmask) << 9) | j) : 0xffffffffu;
+    }
+    warp_bitonic<PER>(v, lane);
+#pragma unroll
+    for (int r = 0; r < PER; r++)
+        if (lane * PER + r < M) we[lane * PER + r] = v[r];
+    __syncwarp();
+}
 
 // Order of two suffixes whose first k symbols agree: compare the following keys, k symbols at
 // a time.  A suffix that runs past the end reads as zeros, which no symbol code equals, so two
@@ -452,7 +521,7 @@ __device__ __noinline__ int suffix_cmp_deep(const uint64_t *__restrict__ pw, int
 // Slow path of the final sort: the calling lane insertion-sorts, by full suffix comparison,
 // every run of equal field whose head sits at one of its slots (lane, lane+32, ...).  Runs are
 // disjoint, so lanes never touch each other's slots.  Returns undecided pairs | overflow << 16.
-__device__ __noinline__ uint32_t fs_sort_runs(uint32_t *we, const uint32_t *wv, uint32_t M, unsigned lane,
+__device__ __noinline__ uint32_t fs_sort_runs(uint32_t *we, const uint2 *__restrict__ wv, uint32_t M, unsigned lane,
                                               const uint64_t *__restrict__ pw, int b, int kb, int k, uint64_t n,
                                               uint32_t idxmask) {
     uint32_t undecided = 0, overflow = 0;
@@ -466,11 +535,11 @@ __device__ __noinline__ uint32_t fs_sort_runs(uint32_t *we, const uint32_t *wv, 
             continue;
         }
         for (uint32_t x = a + 1; x < c; x++) {
-            const uint32_t ex = we[x], sx = wv[ex & 511u] & idxmask;
+            const uint32_t ex = we[x], sx = wv[ex & 511u].y & idxmask;
             const uint64_t kx = extract_key(pw, b, kb, sx);
             uint32_t y = x;
             while (y > a) {
-                const uint32_t ey = we[y - 1], sy = wv[ey & 511u] & idxmask;
+                const uint32_t ey = we[y - 1], sy = wv[ey & 511u].y & idxmask;
                 const uint64_t ky = extract_key(pw, b, kb, sy);
                 int cmp = ky < kx ? -1 : (ky > kx ? 1 : suffix_cmp_deep(pw, b, kb, k, n, sy, sx, 16));
                 undecided += cmp == 0;
@@ -492,7 +561,6 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 4)
     __shared__ FsWarp fs[FS_WARPS];
     FsWarp &W = fs[threadIdx.x >> 5];
     const unsigned lane = lane_id();
-    const unsigned lt = lanemask_lt();
     const uint32_t bk = blockIdx.x * FS_WARPS + (threadIdx.x >> 5);
     if (bk >= nbuckets) return;
     const uint32_t s = starts[bk], M = starts[bk + 1] - s;
@@ -505,82 +573,17 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 4)
     const int fbits = rb < 23 ? rb : 23;
     const int fsh = rb - fbits;
     const uint32_t fmask = (fbits ? (0xffffffffu >> (32 - fbits)) : 0u);
-    uint32_t e[FS_PER];
-    uint32_t rnk[FS_PER / 2]; // two 16-bit ranks per register
-#pragma unroll
-    for (int i = 0; i < FS_PER; i++) {
-        uint32_t j = lane + 32 * i;
-        e[i] = 0;
-        if (j < M) {
-            uint2 r = rec[s + j];
-            W.v[j] = r.y;
-            e[i] = (((r.x >> fsh) & fmask) << 9) | j;
-        }
-    }
-    const int nr = (fbits + 7) / 8;
-    for (int round = 0; round < nr; round++) {
-        const int dsh = 9 + 8 * round;
-        for (int j = lane; j < 128; j += 32) reinterpret_cast<uint32_t *>(W.cnt)[j] = 0;
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < FS_PER; i++) {
-            if (32u * i < M) { // warp-uniform
-                bool valid = lane + 32 * i < M;
-                uint32_t d = (e[i] >> dsh) & 255u;
-                unsigned peers = match_bits<8>(d, valid);
-                uint32_t pre = valid ? W.cnt[d] : 0;
-                __syncwarp();
-                if (valid && (peers & lt) == 0) W.cnt[d] = (uint16_t)(pre + __popc(peers));
-                __syncwarp();
-                uint32_t rk = pre + __popc(peers & lt);
-                rnk[i >> 1] = (i & 1) ? (rnk[i >> 1] | (rk << 16)) : rk;
-            }
-        }
-        // exclusive scan of the 256 counters, 8 per lane
-        uint32_t c[8], run = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            c[q] = W.cnt[lane * 8 + q];
-            run += c[q];
-        }
-        uint32_t excl = warp_incl_sum(run) - run;
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            W.cnt[lane * 8 + q] = (uint16_t)excl;
-            excl += c[q];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < FS_PER; i++) {
-            if (lane + 32 * i < M) W.e[W.cnt[(e[i] >> dsh) & 255u] + ((rnk[i >> 1] >> (16 * (i & 1))) & 0xffffu)] = e[i];
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < FS_PER; i++) {
-            uint32_t j = lane + 32 * i;
-            if (j < M) e[i] = W.e[j];
-        }
-    }
-    if (nr == 0) {
-#pragma unroll
-        for (int i = 0; i < FS_PER; i++)
-            if (lane + 32 * i < M) W.e[lane + 32 * i] = e[i];
-        __syncwarp();
-    }
+    if (M <= 256) fs_sort_bucket<8>(rec + s, M, fsh, fmask, W.e, lane);
+    else fs_sort_bucket<16>(rec + s, M, fsh, fmask, W.e, lane);
     // runs of equal field (rare): the lane holding the head of a run sorts it by full keys
     bool head = false;
-#pragma unroll
-    for (int i = 0; i < FS_PER; i++) {
-        uint32_t j = lane + 32 * i;
-        if (j + 1 < M) {
-            uint32_t f = e[i] >> 9;
-            head |= (W.e[j + 1] >> 9) == f && (j == 0 || (W.e[j - 1] >> 9) != f);
-        }
+    for (uint32_t j = lane; j + 1 < M; j += 32) {
+        const uint32_t f = W.e[j] >> 9;
+        head |= (W.e[j + 1] >> 9) == f && (j == 0 || (W.e[j - 1] >> 9) != f);
     }
     if (__any_sync(TC_FULL, head)) {
         uint32_t r = 0;
-        if (head) r = fs_sort_runs(W.e, W.v, M, lane, pw, b, kb, k, n, packprev ? 0x00ffffffu : 0xffffffffu);
+        if (head) r = fs_sort_runs(W.e, rec + s, M, lane, pw, b, kb, k, n, packprev ? 0x00ffffffu : 0xffffffffu);
         __syncwarp();
         uint32_t und = r & 0xffffu;
         for (int dlt = 16; dlt; dlt >>= 1) und += __shfl_xor_sync(TC_FULL, und, dlt);
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 4)
     }
     // slot 0 of the suffix array belongs to the empty suffix, so bucket slot j is row 1 + s + j
     for (uint32_t j = lane; j < M; j += 32) {
-        uint32_t v = W.v[W.e[j] & 511u];
+        uint32_t v = rec[s + (W.e[j] & 511u)].y; // the bucket was just read: an L1/L2 hit
         uint32_t idx = packprev ? (v & 0x00ffffffu) : v;
         sa[1 + s + j] = idx;
         if (bwt) {
