@@ -294,6 +294,11 @@ def run_b200(args):
         fm = run_fm(args, ctx, stream, world, rank, local, peak)
         if line is not None:
             line["fm_count"] = fm
+    if args.locate:
+        torch.cuda.empty_cache()
+        loc = run_locate(args, ctx, stream, world, rank, local, peak)
+        if line is not None:
+            line["fm_locate"] = loc
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -387,6 +392,93 @@ def run_fm(args, ctx, stream, world, rank, local, peak):
     return out
 
 
+def synth_acgtn(n, seed, stream_device="cuda"):
+    """n bytes of ACGTN (P(N) = 0.01) on the device, generated in slices to bound scratch memory."""
+    import torch
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    step = 1 << 27
+    for o in range(0, n, step):
+        m = min(step, n - o)
+        r = torch.rand(m, device="cuda", generator=g)
+        base = torch.randint(0, 4, (m,), device="cuda", generator=g)
+        out[o:o + m] = torch.where(r < 0.01, torch.tensor(ord("N"), dtype=torch.uint8, device="cuda"), lut[base])
+        del r, base
+    return out
+
+
+def run_locate(args, ctx, stream, world, rank, local, peak):
+    """Config 4: locateFMIndex with a sampled suffix array on a synthetic ACGTN reference,
+    32-bp patterns sharded over the GPUs, index replicated with one NCCL broadcast."""
+    import torch
+    import torch.distributed as dist
+    from text_compression_b200 import multi
+    n, q, m, rate = args.loc_n, args.loc_q, 32, args.fm_rate
+    with torch.cuda.stream(stream):
+        text = synth_acgtn(n, 0xC4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fm = multi.build_replicated(ctx, text, n, rate)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        q_local = q // world
+        g = torch.Generator(device="cuda")
+        g.manual_seed(0xC4 + 1 + rank)
+        offs = torch.randint(0, n - m, (q_local,), device="cuda", generator=g)
+        pats = text[offs[:, None] + torch.arange(m, device="cuda")[None, :]].contiguous()
+        del text
+        off = (torch.arange(q_local + 1, device="cuda", dtype=torch.int64) * m).contiguous()
+        cap = 4 * q_local + 1024
+        hit_off = torch.empty(q_local + 1, dtype=torch.int64, device="cuda")
+        pos = torch.empty(cap, dtype=torch.int64, device="cuda")
+        total = C.c_uint64(0)
+        torch.cuda.synchronize()
+
+        def once():
+            ctx.call("tc_fm_locate_dev", fm.h, C.c_void_p(pats.data_ptr()), C.c_void_p(off.data_ptr()), q_local,
+                     C.c_void_p(hit_off.data_ptr()), C.c_void_p(pos.data_ptr()), cap, C.byref(total))
+
+        for _ in range(3):
+            once()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            once()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        hits = int(total.value)
+        # every pattern was cut from the text, so it must be found at (at least) its own offset
+        ho = hit_off.cpu().numpy()
+        ps = pos[:hits].cpu().numpy()
+        oh = offs.cpu().numpy()
+        ok = all((oh[i] + 1) in ps[ho[i]:ho[i + 1]] for i in range(0, q_local, max(1, q_local // 2000)))
+    pps = world * q_local * args.steps / (ms / 1e3)
+    per_pat = m + 2 * (m - 1) * 32
+    per_hit = 8 + 4 + 32 * (rate - 1) // 2
+    out = {"metric": "fm_locate_patterns_per_s", "value": pps, "unit": "patterns/s", "n_gpus": world,
+           "config": {"workload": f"C4: locateFMIndex, sampled SA (rate {rate}), {n} bp synthetic ACGTN, "
+                                  f"{q_local * world} patterns x {m} bp sharded over GPUs", "sa_sample_rate": rate},
+           "build_s": build_s, "ms_per_batch": ms / args.steps, "hits_per_pattern": hits / max(q_local, 1),
+           "self_hit_check": bool(ok),
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                        "achieved": (q_local * per_pat + hits * per_hit) * args.steps / 1e9 / (ms / 1e3),
+                        "bytes_per_pattern": per_pat, "bytes_per_hit": per_hit},
+           "index_bytes": int(fm.info.blob_bytes)}
+    out["roofline"]["frac"] = out["roofline"]["achieved"] / peak
+    fm.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,6 +489,9 @@ def main():
     ap.add_argument("--fm-n", type=int, default=100_000_000)
     ap.add_argument("--fm-q", type=int, default=10_000_000)
     ap.add_argument("--fm-rate", type=int, default=32)
+    ap.add_argument("--locate", type=int, default=1, help="also run the locate workload (config 4)")
+    ap.add_argument("--loc-n", type=int, default=1_000_000_000)
+    ap.add_argument("--loc-q", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

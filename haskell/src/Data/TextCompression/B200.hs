@@ -83,6 +83,10 @@ foreign import ccall safe "tc_rle_decode"
   c_rle_decode :: Ptr TcCtx -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr Int16 -> Word64 -> Ptr Word64 -> IO CInt
 foreign import ccall safe "tc_bwt_mtf_rle_encode"
   c_bwt_mtf_rle :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr () -> IO CInt
+-- multi-block entry point: copies of neighbouring blocks overlap the kernels of the current one
+foreign import ccall safe "tc_blocks_encode"
+  c_blocks_encode :: Ptr TcCtx -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> CInt -> Ptr (Ptr Word32)
+                  -> Ptr (Ptr Int16) -> Ptr Word64 -> Ptr () -> IO CInt
 foreign import ccall safe "tc_fm_build"
   c_fm_build :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Word32 -> Ptr (Ptr TcFm) -> IO CInt
 foreign import ccall safe "&tc_fm_free" p_fm_free :: FunPtr (Ptr TcFm -> IO ())
