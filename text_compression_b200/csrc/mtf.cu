@@ -159,12 +159,12 @@ __global__ void mtf2_scan_tiles_kernel(uint32_t *__restrict__ lastocc, uint64_t 
     if (c >= VS) return;
     uint64_t k0 = (uint64_t)blockIdx.x * G, k1 = k0 + G < nchunks ? k0 + G : nchunks;
     uint32_t run = 0;
-    for (uint64_t kb = k0; kb < k1; kb += 8) {
-        uint32_t v[8];
+    for (uint64_t kb = k0; kb < k1; kb += 16) {
+        uint32_t v[16];
 #pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = (kb + q < k1) ? lastocc[(kb + q) * VS + c] : 0;
+        for (int q = 0; q < 16; q++) v[q] = (kb + q < k1) ? lastocc[(kb + q) * VS + c] : 0;
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < 16; q++) {
             if (kb + q < k1) lastocc[(kb + q) * VS + c] = run;
             run = max(run, v[q]);
         }
@@ -177,12 +177,12 @@ __global__ void mtf2_scan_top_kernel(uint32_t *__restrict__ tiletot, uint64_t nt
     uint32_t c = threadIdx.x;
     if (c >= VS) return;
     uint32_t run = 0;
-    for (uint64_t tb = 0; tb < ntiles; tb += 16) {
-        uint32_t v[16];
+    for (uint64_t tb = 0; tb < ntiles; tb += 32) {
+        uint32_t v[32];
 #pragma unroll
-        for (int q = 0; q < 16; q++) v[q] = (tb + q < ntiles) ? tiletot[(tb + q) * VS + c] : 0;
+        for (int q = 0; q < 32; q++) v[q] = (tb + q < ntiles) ? tiletot[(tb + q) * VS + c] : 0;
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
+        for (int q = 0; q < 32; q++) {
             if (tb + q < ntiles) tiletot[(tb + q) * VS + c] = run;
             run = max(run, v[q]);
         }

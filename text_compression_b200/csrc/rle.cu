@@ -148,10 +148,16 @@ __global__ void __launch_bounds__(RT)
                     const uint32_t *__restrict__ tile_justx, uint32_t *__restrict__ count, int16_t *__restrict__ rsym,
                     uint64_t cap, uint64_t *__restrict__ d_R) {
     constexpr int ITEMS = In::ITEMS;
-    constexpr int CAP = In::MAX_PER_ITEM * RT * ITEMS + 3; // + one Nothing's second pair + final flush
+    constexpr int CAP = In::MAX_PER_ITEM * RT * ITEMS + 3 + 8; // + one Nothing's second pair + final flush + alignment pad
     __shared__ uint32_t sh[RT / 32 + 1];
-    __shared__ uint32_t s_cnt[CAP];
-    __shared__ int16_t s_sym[CAP];
+    __shared__ __align__(16) uint32_t s_cnt_raw[CAP];
+    __shared__ __align__(16) int16_t s_sym_raw[CAP];
+    // runs are staged so that staged index and global index agree modulo the vector width:
+    // the copy-out below then moves 16 bytes per store
+    const uint64_t goff = tile_off[blockIdx.x];
+    const uint32_t padc = (uint32_t)(goff & 3), pads = (uint32_t)(goff & 7);
+    uint32_t *s_cnt = s_cnt_raw + padc;
+    int16_t *s_sym = s_sym_raw + pads;
     uint64_t base = ((uint64_t)blockIdx.x * RT + threadIdx.x) * ITEMS;
     int c[ITEMS];
     int p0 = NOPREV;
@@ -224,12 +230,38 @@ __global__ void __launch_bounds__(RT)
         }
     }
     __syncthreads();
-    uint64_t goff = tile_off[blockIdx.x];
-    for (uint32_t j = threadIdx.x; j < tile_total; j += RT) {
-        uint64_t g = goff + j;
-        if (g < cap) {
-            count[g] = s_cnt[j];
-            rsym[g] = s_sym[j];
+    const bool vec_ok = goff + tile_total <= cap && (reinterpret_cast<uintptr_t>(count) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(rsym) & 15) == 0;
+    if (vec_ok) {
+        const uint32_t nvc = (padc + tile_total + 3) / 4;
+        uint32_t *gc = count + (goff - padc);
+        for (uint32_t v = threadIdx.x; v < nvc; v += RT) {
+            const uint32_t j0 = 4 * v;
+            if (j0 >= padc && j0 + 4 <= padc + tile_total) {
+                *reinterpret_cast<uint4 *>(gc + j0) = *reinterpret_cast<const uint4 *>(s_cnt_raw + j0);
+            } else {
+                for (uint32_t j = j0; j < j0 + 4; j++)
+                    if (j >= padc && j < padc + tile_total) gc[j] = s_cnt_raw[j];
+            }
+        }
+        const uint32_t nvs = (pads + tile_total + 7) / 8;
+        int16_t *gs = rsym + (goff - pads);
+        for (uint32_t v = threadIdx.x; v < nvs; v += RT) {
+            const uint32_t j0 = 8 * v;
+            if (j0 >= pads && j0 + 8 <= pads + tile_total) {
+                *reinterpret_cast<uint4 *>(gs + j0) = *reinterpret_cast<const uint4 *>(s_sym_raw + j0);
+            } else {
+                for (uint32_t j = j0; j < j0 + 8; j++)
+                    if (j >= pads && j < pads + tile_total) gs[j] = s_sym_raw[j];
+            }
+        }
+    } else {
+        for (uint32_t j = threadIdx.x; j < tile_total; j += RT) {
+            uint64_t g = goff + j;
+            if (g < cap) {
+                count[g] = s_cnt[j];
+                rsym[g] = s_sym[j];
+            }
         }
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;

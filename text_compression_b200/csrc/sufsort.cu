@@ -63,22 +63,55 @@ __device__ __forceinline__ uint64_t extract_key(const uint64_t *__restrict__ pw,
     return v >> (64 - kb);
 }
 
+// One thread packs 64 symbols into exactly B words, so every shift is a compile-time constant.
+template <int B>
 __global__ void __launch_bounds__(256)
-    sa_pack_kernel(const uint8_t *__restrict__ t, uint64_t n, Code256 lut, int b, uint64_t nwords,
-                   uint64_t *__restrict__ pw) {
+    sa_pack_kernel(const uint8_t *__restrict__ t, uint64_t n, Code256 lut, uint64_t nwords, uint64_t *__restrict__ pw) {
     __shared__ uint16_t s_lut[256];
     s_lut[threadIdx.x] = lut.code[threadIdx.x];
     __syncthreads();
-    uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (w >= nwords) return;
-    uint64_t bit0 = w * 64;
-    uint64_t word = 0;
-    for (uint64_t j = bit0 / b; j * b < bit0 + 64; j++) {
-        uint64_t code = j < n ? s_lut[t[j]] : 0;
-        int s = 64 - (int)((int64_t)(j * b) - (int64_t)bit0) - b; // left shift that puts the symbol in place
-        word |= s >= 0 ? (code << s) : (code >> (-s));
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g * B >= nwords) return;
+    const uint64_t base = g * 64;
+    uint32_t by[16]; // 64 text bytes
+    if (base + 64 <= n && (reinterpret_cast<uintptr_t>(t + base) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint4 v = ld_stream_u4(t + base + 16 * q);
+            by[4 * q] = v.x;
+            by[4 * q + 1] = v.y;
+            by[4 * q + 2] = v.z;
+            by[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint64_t i = base + 4 * q + k;
+                if (i < n) w |= (uint32_t)t[i] << (8 * k);
+            }
+            by[q] = w;
+        }
     }
-    pw[w] = word;
+    uint64_t w[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) w[k] = 0;
+#pragma unroll
+    for (int j = 0; j < 64; j++) {
+        const uint64_t code = base + j < n ? (uint64_t)s_lut[(by[j >> 2] >> (8 * (j & 3))) & 0xffu] : 0ull;
+        const int wi = (j * B) >> 6, o = (j * B) & 63;
+        if (o + B <= 64) {
+            w[wi] |= code << (64 - o - B);
+        } else {
+            w[wi] |= code >> (o + B - 64);
+            w[wi + 1] |= code << (128 - o - B);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < B; k++)
+        if (g * B + k < nwords) pw[g * B + k] = w[k];
 }
 
 __global__ void sa_keys_from_packed_kernel(const uint64_t *__restrict__ pw, int b, int kb, uint64_t N,
@@ -769,7 +802,15 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
     uint32_t *g, *ns, *cpos, *d_U;
     TC_TRY(ws_alloc(ctx, nwords, &pw));
     TC_TRY(ws_alloc(ctx, 2, &d_U));
-    TC_LAUNCH(ctx, sa_pack_kernel, (unsigned)ceil_div_u64(nwords, 256), 256, 0, d_text, n, lut, b, nwords, pw);
+    {
+        void (*kpack)(const uint8_t *, uint64_t, Code256, uint64_t, uint64_t *) =
+            b == 1 ? sa_pack_kernel<1> : b == 2 ? sa_pack_kernel<2> : b == 3 ? sa_pack_kernel<3>
+            : b == 4 ? sa_pack_kernel<4> : b == 5 ? sa_pack_kernel<5> : b == 6 ? sa_pack_kernel<6>
+            : b == 7 ? sa_pack_kernel<7> : b == 8 ? sa_pack_kernel<8> : sa_pack_kernel<9>;
+        ctx->prof_bytes_next = n + 8 * nwords;
+        TC_LAUNCH_AS(ctx, "sa_pack_kernel", kpack, (unsigned)ceil_div_u64(ceil_div_u64(nwords, b), 256), 256, 0, d_text, n, lut,
+                     nwords, pw);
+    }
     uint32_t *hU = (uint32_t *)ctx->h_scal;
 
     // ---- sort by key: MSD path on uniform keys (two partition levels + per-warp final sort)
