@@ -232,7 +232,7 @@ __device__ __forceinline__ uint32_t pc_total(const uint8_t *wc, int q, unsigned 
 // K_A: ukey of every suffix 0..n-1 + histogram of the level-1 digit
 constexpr int UK_LUT_MAX = 512; // g-gram table entries (gb <= 9 bits), staged in shared memory
 template <int G>
-__global__ void __launch_bounds__(PC_T)
+__global__ void __launch_bounds__(PC_T, 3)
     uk_keys_kernel(const uint64_t *__restrict__ pw, int b, int kb, int gb, int Gr, const uint2 *__restrict__ lut,
                    uint32_t n, int shift1, uint32_t *__restrict__ ukey, uint32_t *__restrict__ hist1) {
     extern __shared__ __align__(16) uint8_t pc_cnt[];
@@ -246,13 +246,26 @@ __global__ void __launch_bounds__(PC_T)
     __syncthreads();
     const uint32_t tbase = blockIdx.x * PC_TILE + w * PC_WCHUNK;
     uint8_t *mine = wc + lane;
-#pragma unroll 4
-    for (int r = 0; r < PC_ITEMS; r++) {
-        uint32_t i = tbase + r * 32 + lane;
-        if (i < n) {
-            uint32_t u = ukey_of<G>(extract_key32(pw, (uint32_t)b, kb, i), kb, gb, Gr, s_lut);
-            ukey[i] = u;
-            mine[(u >> shift1) * 32]++;
+    // batches of 8 suffixes: all packed-text loads of a batch are issued before any is used
+    for (int r0 = 0; r0 < PC_ITEMS; r0 += 8) {
+        uint64_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t i = tbase + (r0 + q) * 32 + lane;
+            const uint32_t o = (i < n ? i : 0u) * (uint32_t)b;
+            hi[q] = pw[o >> 6];
+            lo[q] = pw[(o >> 6) + 1];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t i = tbase + (r0 + q) * 32 + lane;
+            if (i < n) {
+                const int sh = (int)((i * (uint32_t)b) & 63u);
+                const uint64_t v = sh ? ((hi[q] << sh) | (lo[q] >> (64 - sh))) : hi[q];
+                const uint32_t u = ukey_of<G>(v >> (64 - kb), kb, gb, Gr, s_lut);
+                ukey[i] = u;
+                mine[(u >> shift1) * 32]++;
+            }
         }
     }
     __syncwarp();
@@ -268,7 +281,7 @@ __global__ void __launch_bounds__(PC_T)
 // Partition tiles never straddle a segment (= a bucket of the previous level).  tilebase[s]
 // = first tile of segment s, chunkbase[s] = first counting chunk of segment s.
 constexpr int PT_T = 256;
-constexpr int PT_ITEMS = 16;
+constexpr int PT_ITEMS = 8;
 constexpr int PT_TILE = PT_T * PT_ITEMS;
 constexpr int PT_WARPS = PT_T / 32;
 
@@ -323,7 +336,7 @@ __global__ void __launch_bounds__(PC_T)
     uint8_t *wc = pc_cnt + (size_t)w * 8192;
     pc_zero(wc, lane);
     __syncwarp();
-#pragma unroll 8
+#pragma unroll 16
     for (int r = 0; r < PC_ITEMS; r++) {
         uint32_t i = beg + r * 32 + lane;
         if (i < end) {
@@ -372,7 +385,7 @@ struct PtSmem {
 // not be deterministic -- the final sort orders it).
 // FIRST: the input is ukey[i]; the record becomes (ukey, i | T[i-1] << 24) when packprev.
 template <bool FIRST>
-__global__ void __launch_bounds__(PT_T, 4)
+__global__ void __launch_bounds__(PT_T, 6)
     part_kernel(const uint32_t *__restrict__ ukey_in, const uint8_t *__restrict__ text, int packprev,
                 const uint2 *__restrict__ rec_in, uint2 *__restrict__ rec_out, uint64_t n, int shift, uint32_t dmask,
                 const uint32_t *__restrict__ segstart, const uint32_t *__restrict__ tilebase, int nseg,
@@ -586,7 +599,7 @@ __device__ __noinline__ uint32_t fs_sort_runs(uint32_t *we, const uint2 *__restr
     return (undecided > 0xffffu ? 0xffffu : undecided) | (overflow << 16);
 }
 
-__global__ void __launch_bounds__(FS_WARPS * 32, 4)
+__global__ void __launch_bounds__(FS_WARPS * 32, 5)
     final_sort_kernel(const uint2 *__restrict__ rec, const uint32_t *__restrict__ starts, uint32_t nbuckets, int rb,
                       const uint64_t *__restrict__ pw, int b, int kb, int k, uint64_t n, int packprev,
                       const uint8_t *__restrict__ text, uint32_t *__restrict__ sa, uint8_t *__restrict__ bwt,
