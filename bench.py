@@ -36,7 +36,7 @@ BLOCK = 16 << 20
 NBLOCKS = 12
 METRIC = "bwt_mtf_rle_MB_per_s"
 WORKLOAD = "C2: BWT+MTF+RLE of one 16 MiB synthetic random-byte block per GPU per step"
-CPU_SAMPLE = 1 << 20
+CPU_SAMPLE = 4 << 20
 
 
 def gen_block(seed: int, n: int) -> np.ndarray:
