@@ -336,12 +336,18 @@ __global__ void __launch_bounds__(PC_T)
     uint8_t *wc = pc_cnt + (size_t)w * 8192;
     pc_zero(wc, lane);
     __syncwarp();
-#pragma unroll 16
-    for (int r = 0; r < PC_ITEMS; r++) {
-        uint32_t i = beg + r * 32 + lane;
-        if (i < end) {
-            uint32_t d = (rec[i].x >> shift) & dmask;
-            wc[d * 32 + lane]++;
+    // batches of 16 records: all loads of a batch are issued before any is used
+    for (int r0 = 0; r0 < PC_ITEMS; r0 += 16) {
+        uint32_t x[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            uint32_t i = beg + (r0 + q) * 32 + lane;
+            x[q] = i < end ? rec[i].x : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            uint32_t i = beg + (r0 + q) * 32 + lane;
+            if (i < end) wc[((x[q] >> shift) & dmask) * 32 + lane]++;
         }
     }
     __syncwarp();
