@@ -29,6 +29,16 @@ def blocks_of_rank(n_blocks: int, world_size: int, rank: int):
     return list(range(rank, n_blocks, world_size))
 
 
+def compress_blocks_sharded(texts, with_mtf: bool = True, ctx=None):
+    """Config 5 (multi-block compression): this rank compresses blocks rank, rank + world, ...
+    with the pipelined multi-block call (tc_blocks_encode); no data-path collective.  Returns
+    [(block index, CompressedBlock)] for the blocks this rank owns."""
+    from . import block
+    ws, rk = world()
+    mine = blocks_of_rank(len(texts), ws, rk)
+    return list(zip(mine, block.compress_blocks([texts[b] for b in mine], with_mtf, ctx)))
+
+
 def query_slice(q: int, world_size: int, rank: int):
     """Contiguous chunk [lo, hi) of q queries for `rank` (sizes differ by at most one)."""
     base, rem = divmod(q, world_size)
