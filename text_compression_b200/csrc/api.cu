@@ -271,7 +271,9 @@ int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, 
     present[0] = 1;
     for (int c = 0; c < 256; c++) present[c + 1] = ctx->text_hist[c] != 0;
     TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma, present));
-    return rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R);
+    int rc = rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R); // syncs the stream
+    int rc2 = mtf_finish_pending(ctx);
+    return rc != TC_OK ? rc : rc2;
 }
 
 int compress_host(tc_ctx *ctx, const uint8_t *text, uint64_t n, bool with_mtf, uint32_t *count, int16_t *rsym,

@@ -33,6 +33,13 @@ struct tc_ctx {
     // pinned scalars for small device->host results
     uint64_t *h_scal = nullptr; // 1024 x u64, pinned
     uint64_t launches = 0;
+    // MTF final list still in flight (composed helpers read it after the RLE stage's sync)
+    struct {
+        bool active = false;
+        uint32_t sigma = 0;
+        int16_t alpha[257];
+        int16_t *final_list = nullptr;
+    } mtf_pending;
     uint32_t text_hist[256] = {0}; // byte histogram of the last text handed to the suffix sort
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     char err[512] = {0};

@@ -664,6 +664,25 @@ __global__ void mtfd_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N,
     }
 }
 
+// The final list (ranks) comes back through the pinned scalars.  In the composed helpers
+// (`defer`) the host does not wait here: the RLE stage that follows syncs the stream anyway and
+// mtf_finish_pending() then translates the ranks.  Slot 512.. of h_scal is used by nothing else.
+int mtf_read_final(tc_ctx *ctx, const uint16_t *d_final, uint32_t sigma, const int16_t *alpha, int16_t *final_list,
+                   bool defer) {
+    uint16_t *h_final = (uint16_t *)(ctx->h_scal + 512);
+    TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
+    if (defer) {
+        ctx->mtf_pending.active = true;
+        ctx->mtf_pending.sigma = sigma;
+        memcpy(ctx->mtf_pending.alpha, alpha, sigma * sizeof(int16_t));
+        ctx->mtf_pending.final_list = final_list;
+        return TC_OK;
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
+    return TC_OK;
+}
+
 uint32_t pick_chunk_len(tc_ctx *ctx, uint64_t N, uint32_t lo, uint32_t hi) {
     uint64_t target_threads = (uint64_t)ctx->sm_count * 128;
     uint64_t L = ceil_div_u64(N, target_threads);
@@ -722,13 +741,10 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         TC_LAUNCH(ctx, mtfs_top_kernel, 1, 1024, 0, tot, ntiles, sigma, start_list, d_final);
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
         TC_LAUNCH(ctx, (mtfs_replay_kernel<Src>), (unsigned)ntiles, SM_T, 0, src, lut, N, part, start_list, sigma, d_idx);
-        uint16_t *h_final = (uint16_t *)ctx->h_scal;
-        TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
-        TC_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
         *sigma_out = sigma;
+        int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
         tc_ws_release(ctx, mk);
-        return TC_OK;
+        return rc;
     }
     const uint32_t VS = (sigma + 31) / 32 * 32;
     // chunk length: a multiple of 32, enough chunks to fill the machine with warps
@@ -752,15 +768,23 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
     TC_LAUNCH(ctx, (mtf2_replay_kernel<Src>), cgrid, ENC_WARPS * 32, 0, src, lut, N, L, nchunks, G, sigma, VS, lastocc,
               tiletot, d_idx);
     TC_LAUNCH(ctx, mtf2_final_kernel, 1, 32, 0, finalocc, N, sigma, VS, d_final);
-    uint16_t *h_final = (uint16_t *)ctx->h_scal;
-    TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
     *sigma_out = sigma;
+    int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
     tc_ws_release(ctx, mk);
-    return TC_OK;
+    return rc;
 }
 } // namespace
+
+// after a stream sync: the deferred final list of the last mtf_encode with an alphabet hint
+int mtf_finish_pending(tc_ctx *ctx) {
+    if (!ctx->mtf_pending.active) return TC_OK;
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint16_t *h_final = (const uint16_t *)(ctx->h_scal + 512);
+    for (uint32_t j = 0; j < ctx->mtf_pending.sigma; j++)
+        ctx->mtf_pending.final_list[j] = ctx->mtf_pending.alpha[h_final[j]];
+    ctx->mtf_pending.active = false;
+    return TC_OK;
+}
 
 int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
                            int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint) {
