@@ -39,9 +39,12 @@ WORKLOAD = "C2: BWT+MTF+RLE of one 16 MiB synthetic random-byte block per GPU pe
 CPU_SAMPLE = 4 << 20
 
 
+ALPHABET = "bytes"   # "acgtn" with --workload c5
+
+
 def gen_block(seed: int, n: int) -> np.ndarray:
-    from tests.util import gen_bytes
-    return gen_bytes(seed, n)
+    from tests.util import gen_acgtn, gen_bytes
+    return gen_acgtn(seed, n) if ALPHABET == "acgtn" else gen_bytes(seed, n)
 
 
 def peaks():
@@ -50,6 +53,25 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    ncu --set full capture of this workload (profiles/, produced by tools/make_profiles.sh)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", f"r1_ncu_full_summary_{ALPHABET}.csv")
+    short = kernel.split("<")[0].strip()
+    try:
+        rows = list(csv.reader(open(path)))
+        ix = {h: i for i, h in enumerate(rows[0])}
+        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        for r in rows[2:]:
+            if short in r[ix["Kernel Name"]]:
+                ur, uw = rows[1][ix["dram__bytes_read.sum"]], rows[1][ix["dram__bytes_write.sum"]]
+                return float(r[ix["dram__bytes_read.sum"]]) * unit.get(ur, 1.0) + float(r[ix["dram__bytes_write.sum"]]) * unit.get(uw, 1.0)
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -250,6 +272,7 @@ def run_b200(args):
     if tbytes:
         roofline["achieved"] = tbytes / 1e9 / (tms / 1e3)
         roofline["frac"] = roofline["achieved"] / peak
+    roofline["traffic"] = ncu_traffic(tname)
     N = n + 1
 
     def pass_ms(prefixes):
@@ -258,7 +281,7 @@ def run_b200(args):
     mtf_ms = pass_ms(("mtf",))
     rle_ms = pass_ms(("rle_",))
     bwt_ms = tot_ms / PSTEPS - mtf_ms - rle_ms
-    mtf_bytes = N * 3                     # u8 symbol in, u16 index out (sigma = 257)
+    mtf_bytes = N * 3                     # u8 symbol in, u16 index out
     rle_bytes = N * 2 + 6 * R_last        # u16 index in, (u32 count, i16 symbol) per run out
     passes = {
         "bwt": {"ms": bwt_ms},
@@ -290,6 +313,8 @@ def run_b200(args):
                              "sample": f"first {CPU_SAMPLE >> 20} MiB of block 0, one pass; C restatement of the "
                                        "reference algorithm, single thread (the reference path is sequential)"},
         }
+    if line is not None and args.c1:
+        line["c1_roundtrip"] = run_c1(ctx)
     if args.fm and world >= 1:
         fm = run_fm(args, ctx, stream, world, rank, local, peak)
         if line is not None:
@@ -479,6 +504,35 @@ def run_locate(args, ctx, stream, world, rank, local, peak):
     return out
 
 
+def run_c1(ctx):
+    """Config 1: toBWT -> toMTF -> toRLE and the inverse on a 64 KiB ACGT ByteString, host buffers
+    in and out (a latency case: one small block), against the CPU restatement."""
+    from tests.util import gen_acgt
+    from text_compression_b200 import block
+    from oracle import oracle as orc
+    text = gen_acgt(0xC1, 65536)
+    blk = block.compress_bwt_mtf_rle(text, ctx)
+    assert block.decompress(blk, ctx) == text.tobytes()
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        blk = block.compress_bwt_mtf_rle(text, ctx)
+    t_enc = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        block.decompress(blk, ctx)
+    t_dec = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    bwt = orc.bwt_encode(text)
+    idx, fin = orc.mtf_encode(bwt)
+    cnt, sym = orc.rle_encode(idx.astype(np.int16))
+    t_cpu_enc = time.perf_counter() - t0
+    same = blk.counts.tolist() == cnt.tolist() and blk.syms.tolist() == sym.tolist() and blk.final_list.tolist() == fin.tolist()
+    return {"workload": "C1: 64 KiB ACGT, BWT->MTF->RLE and inverse, host buffers, one call each",
+            "encode_us": 1e6 * t_enc, "decode_us": 1e6 * t_dec, "cpu_port_encode_us": 1e6 * t_cpu_enc,
+            "identical_to_cpu_port": bool(same), "runs": int(blk.R)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -490,11 +544,18 @@ def main():
     ap.add_argument("--fm-q", type=int, default=10_000_000)
     ap.add_argument("--fm-rate", type=int, default=32)
     ap.add_argument("--locate", type=int, default=1, help="also run the locate workload (config 4)")
+    ap.add_argument("--c1", type=int, default=1, help="also time the 64 KiB round trip (config 1)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: random-byte blocks (the headline); c5: ACGTN blocks (multi-block genome text)")
     ap.add_argument("--loc-n", type=int, default=1_000_000_000)
     ap.add_argument("--loc-q", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    global ALPHABET, WORKLOAD
+    if args.workload == "c5":
+        ALPHABET = "acgtn"
+        WORKLOAD = "C5: BWT+MTF+RLE of 16 MiB synthetic ACGTN blocks, one block per GPU per step (blocks round-robin over GPUs)"
     if args.impl == "reference":
         run_reference(args)
     else:
