@@ -22,6 +22,7 @@ struct InU8 {
     const uint8_t *p;
     uint64_t primary;
     static constexpr int ITEMS = 16;
+    static constexpr bool HAS_NOTHING = true;
     static constexpr int MAX_PER_ITEM = 1; // a single Nothing: at most TILE + 1 pairs + the flush
     __device__ __forceinline__ int at(uint64_t i) const { return i == primary ? -1 : (int)p[i]; }
     __device__ __forceinline__ void load(uint64_t base, uint64_t N, int *c) const {
@@ -45,6 +46,7 @@ template <bool SIGNED>
 struct In16 {
     const uint16_t *p;
     static constexpr int ITEMS = SIGNED ? 8 : 16;
+    static constexpr bool HAS_NOTHING = SIGNED; // the unsigned index stream has no Nothing: plain run boundaries
     static constexpr int MAX_PER_ITEM = SIGNED ? 2 : 1; // every position may be a Nothing (2 pairs)
     __device__ __forceinline__ int cvt(uint32_t h) const {
         if (SIGNED) {
@@ -89,23 +91,31 @@ __global__ void __launch_bounds__(RT)
     if (base < N) {
         in.load(base, N, c);
         int p = base == 0 ? NOPREV : in.at(base - 1);
+        const uint32_t b32 = (uint32_t)base;
+        const int lim = base + ITEMS <= N ? ITEMS : (int)(N - base); // items of this thread inside the input
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
-            uint64_t i = base + k;
-            if (i < N) {
-                pairs += n_emit(c[k], p);
-                if (c[k] >= 0) {
-                    lj = (uint32_t)i + 1;
-                    if (p < 0 || p != c[k]) lh = (uint32_t)i + 1;
+            if (k < lim) {
+                if (In::HAS_NOTHING) {
+                    pairs += n_emit(c[k], p);
+                    if (c[k] >= 0) {
+                        lj = b32 + k + 1;
+                        if (p < 0 || p != c[k]) lh = b32 + k + 1;
+                    }
+                } else { // no Nothing in the stream: a pair per change of symbol
+                    if (p != c[k]) {
+                        lh = b32 + k + 1;
+                        pairs += p != NOPREV;
+                    }
                 }
                 p = c[k];
             }
         }
     }
-    uint32_t tp, th, tj;
+    uint32_t tp, th, tj = 0;
     block_excl_sum<uint32_t, RT>(pairs, sh, &tp);
     block_excl_max<uint32_t, RT>(lh, 0u, sh, &th);
-    block_excl_max<uint32_t, RT>(lj, 0u, sh, &tj);
+    if (In::HAS_NOTHING) block_excl_max<uint32_t, RT>(lj, 0u, sh, &tj);
     if (threadIdx.x == 0) {
         tile_pairs[blockIdx.x] = tp;
         tile_head[blockIdx.x] = th;
@@ -162,18 +172,26 @@ __global__ void __launch_bounds__(RT)
     int c[ITEMS];
     int p0 = NOPREV;
     uint32_t pairs = 0, lh = 0, lj = 0;
+    const uint32_t b32 = (uint32_t)base;
+    const int lim = base >= N ? 0 : (base + ITEMS <= N ? ITEMS : (int)(N - base));
     if (base < N) {
         in.load(base, N, c);
         p0 = base == 0 ? NOPREV : in.at(base - 1);
         int p = p0;
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
-            uint64_t i = base + k;
-            if (i < N) {
-                pairs += n_emit(c[k], p);
-                if (c[k] >= 0) {
-                    lj = (uint32_t)i + 1;
-                    if (p < 0 || p != c[k]) lh = (uint32_t)i + 1;
+            if (k < lim) {
+                if (In::HAS_NOTHING) {
+                    pairs += n_emit(c[k], p);
+                    if (c[k] >= 0) {
+                        lj = b32 + k + 1;
+                        if (p < 0 || p != c[k]) lh = b32 + k + 1;
+                    }
+                } else {
+                    if (p != c[k]) {
+                        lh = b32 + k + 1;
+                        pairs += p != NOPREV;
+                    }
                 }
                 p = c[k];
             }
@@ -183,39 +201,50 @@ __global__ void __launch_bounds__(RT)
     uint32_t tile_total;
     uint32_t o = block_excl_sum<uint32_t, RT>(pairs, sh, &tile_total);
     uint32_t H = block_excl_max<uint32_t, RT>(lh, 0u, sh, (uint32_t *)nullptr);
-    uint32_t J = block_excl_max<uint32_t, RT>(lj, 0u, sh, (uint32_t *)nullptr);
+    uint32_t J = 0;
+    if (In::HAS_NOTHING) J = block_excl_max<uint32_t, RT>(lj, 0u, sh, (uint32_t *)nullptr);
     H = max(H, tile_headx[blockIdx.x]);
-    J = max(J, tile_justx[blockIdx.x]);
+    if (In::HAS_NOTHING) J = max(J, tile_justx[blockIdx.x]);
     if (base < N) {
         int p = p0;
+        const bool owns_last = base + ITEMS >= N; // this thread holds position N-1
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
-            uint64_t i = base + k;
-            if (i < N) {
-                int ck = c[k];
-                if (p != NOPREV) {
-                    if (ck < 0) {
-                        if (p >= 0) {
-                            s_cnt[o] = (uint32_t)i - (H - 1);
+            if (k < lim) {
+                const uint32_t i = b32 + k;
+                const int ck = c[k];
+                if (In::HAS_NOTHING) {
+                    if (p != NOPREV) {
+                        if (ck < 0) {
+                            if (p >= 0) {
+                                s_cnt[o] = i - (H - 1);
+                                s_sym[o] = (int16_t)p;
+                            } else {
+                                s_cnt[o] = J == 0 ? 1u : J - H + 1;
+                                s_sym[o] = -1;
+                            }
+                            s_cnt[o + 1] = 1;
+                            s_sym[o + 1] = -1;
+                            o += 2;
+                        } else if (p >= 0 && p != ck) {
+                            s_cnt[o] = i - (H - 1);
                             s_sym[o] = (int16_t)p;
-                        } else {
-                            s_cnt[o] = J == 0 ? 1u : J - H + 1;
-                            s_sym[o] = -1;
+                            o += 1;
                         }
-                        s_cnt[o + 1] = 1;
-                        s_sym[o + 1] = -1;
-                        o += 2;
-                    } else if (p >= 0 && p != ck) {
-                        s_cnt[o] = (uint32_t)i - (H - 1);
+                    }
+                    if (ck >= 0) {
+                        J = i + 1;
+                        if (p < 0 || p != ck) H = i + 1;
+                    }
+                } else if (p != ck) {
+                    if (p != NOPREV) {
+                        s_cnt[o] = i - (H - 1);
                         s_sym[o] = (int16_t)p;
                         o += 1;
                     }
+                    H = i + 1;
                 }
-                if (ck >= 0) {
-                    J = (uint32_t)i + 1;
-                    if (p < 0 || p != ck) H = (uint32_t)i + 1;
-                }
-                if (i == N - 1) { // end-of-input flush (src/Data/RLE/Internal.hs:125-130)
+                if (owns_last && k == lim - 1) { // end-of-input flush (src/Data/RLE/Internal.hs:125-130)
                     if (ck >= 0) {
                         s_cnt[o] = (uint32_t)N - (H - 1);
                         s_sym[o] = (int16_t)ck;
