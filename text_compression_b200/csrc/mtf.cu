@@ -4,15 +4,17 @@
 // Symbols are first mapped to alphabet ranks 0..sigma-1 (nubSeq', :79-99: sorted,
 // Nothing first), so the initial list L0 is the identity permutation.
 //
-// Encode, generic alphabet (sigma <= 257):
-//   K1  thread per chunk: recency list of the chunk (distinct ranks, most recent first)
-//   K2a warp per tile of chunks: exclusive chain of   acc <- r ++ (acc \ r)   inside the tile
-//   K2b one warp: exclusive chain over tiles starting from L0 (also yields the FINAL list,
-//       the second component seqToMTF returns)
-//   K3  thread per chunk: replay.  The list is never materialised: every symbol owns a
-//       time slot (virtual slots for the incoming order, then one slot per position) and a
-//       bitmap marks the slots that are "latest occurrence of their symbol".  The MTF index
-//       of c is popcount(bitmap in (last[c], now)) -- O(gap/32) instead of O(sigma).
+// Encode, sigma <= 8 (ACGT(N) + sentinel): the list is one register, see "small alphabets".
+// Encode, generic alphabet (sigma <= 257): the list state at a position is fully described by
+// the last occurrence of every rank before it (more recent = closer to the front), so
+//   K1  warp per chunk: last occurrence of every rank inside the chunk
+//   K2  exclusive max-scan of those rows over chunks (tiles of 64 chunks, then over tiles);
+//       the row after the last chunk gives the FINAL list, seqToMTF's second component
+//   K3  warp per chunk: replay, 32 positions per step.  The list is never materialised: every
+//       rank owns a time slot (virtual slots for the incoming order, then one slot per
+//       position) and a bitmap marks the slots that are "latest occurrence of their rank".
+//       The MTF index of c is popcount(bitmap above last[c]); ranks touched earlier in the
+//       same step are corrected with ballots.
 // Decode: same chunk/tile structure; a chunk's summary is the permutation it applies to
 //   list positions, composition is a gather.
 // Algorithmic bytes: N * (1 + w_idx) (u8 symbols in, u16 indices out here: 3N).
@@ -34,7 +36,6 @@ struct SrcU8 {
     const uint8_t *p;
     uint64_t primary;
     __device__ __forceinline__ int at(uint64_t i) const { return i == primary ? 0 : (int)p[i] + 1; }
-    static constexpr int VEC = 16;
     __device__ __forceinline__ bool can_vec(uint64_t base) const {
         return (reinterpret_cast<uintptr_t>(p + base) & 15) == 0;
     }
@@ -56,7 +57,6 @@ struct SrcI16 {
         int v = p[i];
         return v < 0 ? 0 : (v & 0xff) + 1;
     }
-    static constexpr int VEC = 16;
     __device__ __forceinline__ bool can_vec(uint64_t base) const {
         return (reinterpret_cast<uintptr_t>(p + base) & 15) == 0;
     }
@@ -100,7 +100,6 @@ __global__ void __launch_bounds__(256) mtf_presence_kernel(Src src, uint64_t N, 
 // word w of thread t lives at sm[w * blockDim.x + t]: conflict-free for any per-thread index.
 struct TState {
     uint32_t *sm;
-    __device__ __forceinline__ uint32_t &word(int w) const { return sm[w * blockDim.x + threadIdx.x]; }
     __device__ __forceinline__ uint16_t get16(int i) const {
         return reinterpret_cast<const uint16_t *>(&sm[(i >> 1) * blockDim.x + threadIdx.x])[i & 1];
     }

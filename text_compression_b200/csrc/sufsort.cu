@@ -6,11 +6,15 @@
 //      symbol, so the key of suffix i (its first k = 64/b symbols: 21 for ACGT(N), 7 for
 //      bytes) is two 64-bit loads and a funnel shift.
 //   2. sort all suffixes by key.  Two paths:
-//      MSD path (balanced inputs): counting sort on a <= 24-bit key prefix with global
-//        atomics (not stable -- it need not be), then every bucket (<= 1024 suffixes) is sorted
-//        by one warp with a bitonic network in shared memory.  ~3 sweeps over the data instead
-//        of 8 LSD passes; the LSD passes are ALU-bound on ballot matching (profiles/README.md).
-//      LSD path (fallback: skewed or very large inputs): 8-bit radix passes (radix.cu).
+//      MSD path (4 Ki <= n <= 25 Mi, the block sizes of the compressor): the radix is taken
+//        from a 32-bit *uniform key* -- the arithmetic code of the suffix's first symbols under
+//        the text's own symbol frequencies -- so two 8-bit partition levels give 65,536 evenly
+//        filled buckets for any memoryless text; one warp then sorts a bucket with a bitonic
+//        network in registers and writes the suffix array and the BWT bytes.  Ties in the
+//        32-bit key are settled with the packed 63-bit keys and, beyond them, by comparing the
+//        suffixes k symbols at a time.  See "MSD path on uniform keys" below.
+//      LSD path (tiny or huge inputs, and texts whose buckets overflow, i.e. strongly
+//        correlated or repetitive text): 8-bit radix passes over the packed keys (radix.cu).
 //   3. group heads (key != previous key) -> running max = group id = rank; suffixes in
 //      singleton groups are final.
 //   4. while unresolved suffixes remain: compact them, key2 = (group << 32 | rank[i + h]),
