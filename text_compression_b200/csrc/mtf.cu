@@ -399,7 +399,6 @@ __global__ void __launch_bounds__(32)
 // an exclusive scan: inside the CTA by shuffles and shared memory (K1), over CTAs by one CTA (K2).
 constexpr int SM_L = 64;            // symbols per thread
 constexpr int SM_T = 256;           // threads per CTA
-constexpr int SM_TILE = SM_L * SM_T;
 struct Summ {
     uint32_t list, mask;
 };

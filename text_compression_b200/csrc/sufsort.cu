@@ -194,15 +194,6 @@ __device__ __forceinline__ uint32_t ukey_of(uint64_t key, int kb, int gb, int Gr
     }
     return x;
 }
-// extract_key for texts whose bit offsets fit 32 bits
-__device__ __forceinline__ uint64_t extract_key32(const uint64_t *__restrict__ pw, uint32_t b, int kb, uint32_t i) {
-    const uint32_t o = i * b;
-    const uint64_t hi = pw[o >> 6], lo = pw[(o >> 6) + 1];
-    const int sh = (int)(o & 63u);
-    uint64_t v = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
-    return v >> (64 - kb);
-}
-
 // bytes of a uint4 summed (each field of the result holds at most 16 * 255)
 __device__ __forceinline__ uint32_t byte_sum16(uint4 v) {
     uint32_t a = (v.x & 0x00ff00ffu) + ((v.x >> 8) & 0x00ff00ffu);
