@@ -172,6 +172,12 @@ __global__ void __launch_bounds__(1024) uk_lut_kernel(SymProb sp, int sigma, int
     }
 }
 
+// Shared-memory slot of g-gram e.  Symbol codes use 1..sigma of the 2^b values of a field, so
+// the raw indices of the g-grams that occur cluster on a few banks (ACGTN in 3-bit fields: 10
+// of 16 bank pairs, 79 us of bank-conflict replays per SM in uk_keys); folding the upper index
+// bits into the lower ones spreads them.
+__device__ __forceinline__ uint32_t lut_slot(uint32_t e) { return e ^ (e >> 4); }
+
 // G lookups of gb key bits each, from the top of the (right-aligned, kb-bit) key; G = 0: runtime Gr
 template <int G>
 __device__ __forceinline__ uint32_t ukey_of(uint64_t key, int kb, int gb, int Gr, const uint2 *lut /*shared*/) {
@@ -181,13 +187,13 @@ __device__ __forceinline__ uint32_t ukey_of(uint64_t key, int kb, int gb, int Gr
     if (G > 0) {
 #pragma unroll
         for (int j = 0; j < G; j++, sh -= gb) {
-            uint2 e = lut[(uint32_t)(key >> sh) & m];
+            uint2 e = lut[lut_slot((uint32_t)(key >> sh) & m)];
             x += __umulhi(r, e.x);
             r = __umulhi(r, e.y);
         }
     } else {
         for (int j = 0; j < Gr; j++, sh -= gb) {
-            uint2 e = lut[(uint32_t)(key >> sh) & m];
+            uint2 e = lut[lut_slot((uint32_t)(key >> sh) & m)];
             x += __umulhi(r, e.x);
             r = __umulhi(r, e.y);
         }
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(PC_T, 3)
     __shared__ uint2 s_lut[UK_LUT_MAX];
     const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
-    for (int j = threadIdx.x; j < (1 << gb); j += PC_T) s_lut[j] = lut[j];
+    for (int j = threadIdx.x; j < (1 << gb); j += PC_T) s_lut[lut_slot(j)] = lut[j];
     uint8_t *wc = pc_cnt + (size_t)w * 8192;
     pc_zero(wc, lane);
     __syncthreads();
