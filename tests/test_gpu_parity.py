@@ -251,6 +251,36 @@ def test_suffix_sort_msd_and_fallback(ctx, orc, name, text, monkeypatch):
     assert primary2 == primary and np.array_equal(np.delete(bwt2, primary2), np.delete(bwt, primary))
 
 
+def test_suffix_sort_fuzz_msd_vs_lsd(ctx, orc, monkeypatch):
+    """Random sizes, alphabet sizes (every code width b = 1..9) and symbol skews: the MSD path
+    must give the same suffix array as the LSD path, and both the oracle's on the smaller ones."""
+    from text_compression_b200 import _lib
+    from text_compression_b200.bwt import bwt_u8
+    rng = np.random.default_rng(2024)
+    monkeypatch.setenv("TC_B200_NO_MSD", "1")
+    c2 = _lib.Context(0)
+    try:
+        sigmas = [1, 2, 3, 4, 7, 8, 15, 16, 31, 33, 64, 100, 128, 200, 255, 256]
+        for trial, sigma in enumerate(sigmas * 2):
+            n = int(rng.integers(4096, 3_000_000 if trial % 4 == 0 else 300_000))
+            alpha = rng.choice(256, size=sigma, replace=False).astype(np.uint8)
+            if trial % 3 == 0:
+                p = rng.random(sigma) ** 4 + 1e-6     # heavily skewed frequencies
+                p /= p.sum()
+            else:
+                p = np.full(sigma, 1.0 / sigma)
+            text = alpha[rng.choice(sigma, size=n, p=p)]
+            bwt, primary, sa = bwt_u8(text, want_sa=True, ctx=ctx)
+            bwt2, primary2, sa2 = bwt_u8(text, want_sa=True, ctx=c2)
+            assert primary == primary2 and np.array_equal(sa, sa2), (trial, sigma, n)
+            assert np.array_equal(np.delete(bwt, primary), np.delete(bwt2, primary2)), (trial, sigma, n)
+            if n <= 60_000 and sigma > 1:
+                _, want_sa = orc.bwt_encode(text, want_sa=True)
+                assert np.array_equal(sa, want_sa), (trial, sigma, n)
+    finally:
+        c2.close()
+
+
 def test_block_over_16mib_roundtrip(ctx):
     """n > 2^24: the record no longer has room for the preceding byte, so the last sort level
     gathers the BWT symbols from the text instead."""
