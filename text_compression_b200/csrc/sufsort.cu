@@ -618,6 +618,8 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 5)
     if (bk >= nbuckets) return;
     const uint32_t s = starts[bk], M = starts[bk + 1] - s;
     if (M == 0) return;
+    // once any bucket has overflowed the whole sort is redone by the general path: stop working
+    if (*reinterpret_cast<volatile uint32_t *>(&flags[FL_OVERFLOW])) return;
     if (M > FS_CAP) {
         if (lane == 0) atomicOr(&flags[FL_OVERFLOW], 1u);
         return;
@@ -630,9 +632,17 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 5)
     else fs_sort_bucket<16>(rec + s, M, fsh, fmask, W.e, lane);
     // runs of equal field (rare): the lane holding the head of a run sorts it by full keys
     bool head = false;
+    uint32_t eqpairs = 0;
     for (uint32_t j = lane; j + 1 < M; j += 32) {
         const uint32_t f = W.e[j] >> 9;
-        head |= (W.e[j + 1] >> 9) == f && (j == 0 || (W.e[j - 1] >> 9) != f);
+        const bool eq = (W.e[j + 1] >> 9) == f;
+        eqpairs += eq;
+        head |= eq && (j == 0 || (W.e[j - 1] >> 9) != f);
+    }
+    for (int dlt = 16; dlt; dlt >>= 1) eqpairs += __shfl_xor_sync(TC_FULL, eqpairs, dlt);
+    if (eqpairs > 48) { // memoryless text has one or two tied pairs per bucket: this is correlated text
+        if (lane == 0) atomicOr(&flags[FL_OVERFLOW], 1u);
+        return;
     }
     if (__any_sync(TC_FULL, head)) {
         uint32_t r = 0;
