@@ -590,6 +590,165 @@ __global__ void mtfd_perm_kernel(const uint16_t *__restrict__ idx, uint64_t N, u
     for (int j = 0; j < (int)sigma; j++) perm[k * sigma + j] = lst.get16(j);
 }
 
+// ---- decode, small alphabets (sigma <= 8) -------------------------------------------------------
+// Mirror of the small-alphabet encoder: the list of *initial-list positions* is one register
+// (nibble j = which entry of the sorted alphabet sits at list position j).  A chunk's effect is
+// the permutation it leaves behind when run on the identity; chunk A then chunk B composes as
+// (A . B)[j] = A[B[j]] (a nibble gather), so the incoming arrangement of every chunk is an exclusive
+// scan: inside the CTA by shuffles + shared memory, over CTAs by one CTA.
+__device__ __forceinline__ uint32_t nib_take(uint32_t &P, uint32_t r) { // entry at position r moves to the front
+    const uint32_t sh = 4u * r;
+    const uint32_t v = (P >> sh) & 15u;
+    const uint32_t low = (1u << sh) - 1u;
+    P = (P & ~((low << 4) | 0xFu)) | ((P & low) << 4) | v;
+    return v;
+}
+__device__ __forceinline__ uint32_t nib_compose(uint32_t A, uint32_t B) { // arrangement A, then permutation B
+    uint32_t out = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) out |= ((A >> (4u * ((B >> (4 * j)) & 15u))) & 15u) << (4 * j);
+    return out;
+}
+__device__ __forceinline__ void smd_load(const uint16_t *__restrict__ idx, uint64_t base, uint64_t N, int q,
+                                         uint32_t *r /*16*/) {
+    const uint64_t b0 = base + (uint64_t)q * 16;
+    if (b0 + 16 <= N && (reinterpret_cast<uintptr_t>(idx + b0) & 15) == 0) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint4 v = *reinterpret_cast<const uint4 *>(idx + b0 + 8 * h);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) r[8 * h + k] = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) r[k] = b0 + k < N ? idx[b0 + k] : 0xffffffffu;
+    }
+}
+
+__global__ void __launch_bounds__(SM_T)
+    mtfds_perm_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t sigma, uint32_t *__restrict__ part,
+                      uint32_t *__restrict__ tot, uint32_t *__restrict__ err) {
+    __shared__ uint32_t wsum[SM_T / 32];
+    const uint64_t chunk = (uint64_t)blockIdx.x * SM_T + threadIdx.x;
+    const uint64_t base = chunk * SM_L;
+    uint32_t P = 0x76543210u;
+    bool bad = false;
+    if (base < N) {
+#pragma unroll
+        for (int q = 0; q < SM_L / 16; q++) {
+            uint32_t r[16];
+            smd_load(idx, base, N, q, r);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (r[k] != 0xffffffffu) {
+                    uint32_t x = r[k];
+                    if (x >= sigma) {
+                        bad = true;
+                        x = 0;
+                    }
+                    nib_take(P, x);
+                }
+            }
+        }
+    }
+    if (bad) atomicMax(err, 1u);
+    const unsigned lane = lane_id();
+    uint32_t v = P;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(TC_FULL, v, d);
+        if (lane >= (unsigned)d) v = nib_compose(o, v);
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane == 31) wsum[w] = v;
+    uint32_t ex = __shfl_up_sync(TC_FULL, v, 1);
+    if (lane == 0) ex = 0x76543210u;
+    __syncthreads();
+    uint32_t pre = 0x76543210u;
+    for (int ww = 0; ww < w; ww++) pre = nib_compose(pre, wsum[ww]);
+    if (base < N) part[chunk] = nib_compose(pre, ex);
+    if (threadIdx.x == SM_T - 1) tot[blockIdx.x] = nib_compose(pre, v);
+}
+
+__global__ void __launch_bounds__(1024)
+    mtfds_top_kernel(const uint32_t *__restrict__ tot, uint64_t ntiles, uint32_t *__restrict__ start) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry_s;
+    const unsigned lane = lane_id();
+    const int w = threadIdx.x >> 5;
+    uint32_t carry = 0x76543210u;
+    for (uint64_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        const uint64_t t = b0 + threadIdx.x;
+        uint32_t v = t < ntiles ? tot[t] : 0x76543210u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(TC_FULL, v, d);
+            if (lane >= (unsigned)d) v = nib_compose(o, v);
+        }
+        if (lane == 31) wsum[w] = v;
+        uint32_t ex = __shfl_up_sync(TC_FULL, v, 1);
+        if (lane == 0) ex = 0x76543210u;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t x = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(TC_FULL, x, d);
+                if (lane >= (unsigned)d) x = nib_compose(o, x);
+            }
+            uint32_t xe = __shfl_up_sync(TC_FULL, x, 1);
+            if (lane == 0) xe = 0x76543210u;
+            wsum[lane] = nib_compose(carry, xe);
+            if (lane == 31) carry_s = nib_compose(carry, x);
+        }
+        __syncthreads();
+        if (t < ntiles) start[t] = nib_compose(wsum[w], ex);
+        carry = carry_s;
+        __syncthreads();
+    }
+}
+
+struct List8 {
+    int16_t sym[8];
+};
+__global__ void __launch_bounds__(SM_T)
+    mtfds_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t sigma, const uint32_t *__restrict__ part,
+                        const uint32_t *__restrict__ start, List8 l0, int16_t *__restrict__ out) {
+    const uint64_t chunk = (uint64_t)blockIdx.x * SM_T + threadIdx.x;
+    const uint64_t base = chunk * SM_L;
+    if (base >= N) return;
+    uint32_t P = nib_compose(start[blockIdx.x], part[chunk]);
+    // the eight possible symbols, two per register: sym(v) = (pk[v >> 1] >> (16 * (v & 1))) & 0xffff
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) pk[j] = (uint32_t)(uint16_t)l0.sym[2 * j] | ((uint32_t)(uint16_t)l0.sym[2 * j + 1] << 16);
+#pragma unroll
+    for (int q = 0; q < SM_L / 16; q++) {
+        uint32_t r[16];
+        smd_load(idx, base, N, q, r);
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            uint32_t x = r[k] < sigma ? r[k] : 0u; // out-of-range indices were reported by the first pass
+            uint32_t v = r[k] != 0xffffffffu ? nib_take(P, x) : 0u;
+            uint32_t w = (v & 2u) ? ((v & 4u) ? pk[3] : pk[1]) : ((v & 4u) ? pk[2] : pk[0]);
+            uint32_t s = (v & 1u) ? (w >> 16) : (w & 0xffffu);
+            o[k >> 1] = (k & 1) ? (o[k >> 1] | (s << 16)) : s;
+        }
+        const uint64_t b0 = base + (uint64_t)q * 16;
+        if (b0 + 16 <= N && (reinterpret_cast<uintptr_t>(out + b0) & 15) == 0) {
+            uint4 *dst = reinterpret_cast<uint4 *>(out + b0);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (b0 + k < N) out[b0 + k] = (int16_t)((o[k >> 1] >> (16 * (k & 1))) & 0xffffu);
+        }
+    }
+}
+
 // D2a: exclusive chain of permutations inside a tile: acc'[j] = acc[perm[j]].
 __global__ void __launch_bounds__(128)
     mtfd_tile_chain_kernel(const uint16_t *__restrict__ perm, uint64_t nchunks, uint32_t G, uint32_t sigma,
@@ -809,6 +968,26 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
     for (int c = 0; c < SIGMAX; c++)
         if (seen[c]) l0.sym[sigma++] = (int16_t)(c - 1);
     WsMark mk = tc_ws_mark(ctx);
+    if (sigma <= 8) { // the list fits one register
+        const uint64_t nch = ceil_div_u64(N, SM_L), nt = ceil_div_u64(nch, SM_T);
+        uint32_t *part, *tot, *start, *d_err;
+        TC_TRY(ws_alloc(ctx, nt * SM_T, &part));
+        TC_TRY(ws_alloc(ctx, nt, &tot));
+        TC_TRY(ws_alloc(ctx, nt, &start));
+        TC_TRY(ws_alloc(ctx, 1, &d_err));
+        TC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream));
+        List8 l8;
+        for (int j = 0; j < 8; j++) l8.sym[j] = j < (int)sigma ? l0.sym[j] : (int16_t)0;
+        TC_LAUNCH(ctx, mtfds_perm_kernel, (unsigned)nt, SM_T, 0, d_idx, N, sigma, part, tot, d_err);
+        TC_LAUNCH(ctx, mtfds_top_kernel, 1, 1024, 0, tot, nt, start);
+        ctx->prof_bytes_next = 4 * N;
+        TC_LAUNCH(ctx, mtfds_replay_kernel, (unsigned)nt, SM_T, 0, d_idx, N, sigma, part, start, l8, d_sym);
+        uint32_t *h_err = (uint32_t *)ctx->h_scal;
+        TC_TRY(tc_d2h_small(ctx, h_err, d_err, sizeof(uint32_t)));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_ws_release(ctx, mk);
+        return h_err[0] ? TC_E_INDEX : TC_OK;
+    }
     const uint32_t L = pick_chunk_len(ctx, N, 64, 512);
     const uint64_t nchunks = ceil_div_u64(N, L);
     const uint32_t G = 128;
