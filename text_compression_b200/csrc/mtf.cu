@@ -108,6 +108,41 @@ struct TState {
     }
 };
 
+// Move list entry r (16-bit entries, two per word) to the front and return it.  Entries 0..r-1
+// shift up by one: word w becomes (w << 16) | (w-1 >> 16), one load, one funnel shift and one
+// store per TWO entries, the previous word carried in a register.
+__device__ __forceinline__ uint32_t list_take16(const TState &lst, uint32_t r) {
+    const int wr = (int)(r >> 1);
+    uint32_t cur = lst.sm[wr * blockDim.x + threadIdx.x];
+    const uint32_t sym = (r & 1u) ? (cur >> 16) : (cur & 0xffffu);
+    if (r == 0) return sym;
+    const unsigned T = blockDim.x, t = threadIdx.x;
+    int w = wr;
+    if (!(r & 1u) && w > 0) { // even r: entry r+1 (upper half of word wr) stays
+        const uint32_t prev = lst.sm[(w - 1) * T + t];
+        lst.sm[w * T + t] = (cur & 0xffff0000u) | (prev >> 16);
+        cur = prev;
+        w--;
+    }
+    // eight words per trip: the loads are issued before the (possibly aliasing) stores
+    for (; w >= 8; w -= 8) {
+        uint32_t p[9];
+        p[0] = cur;
+#pragma unroll
+        for (int q = 1; q <= 8; q++) p[q] = lst.sm[(w - q) * T + t];
+#pragma unroll
+        for (int q = 0; q < 8; q++) lst.sm[(w - q) * T + t] = __funnelshift_l(p[q + 1], p[q], 16); // (p[q] << 16) | (p[q+1] >> 16)
+        cur = p[8];
+    }
+    for (; w > 0; w--) {
+        const uint32_t prev = lst.sm[(w - 1) * T + t];
+        lst.sm[w * T + t] = __funnelshift_l(prev, cur, 16);
+        cur = prev;
+    }
+    lst.sm[threadIdx.x] = (cur << 16) | sym; // word 0: entry 0 = the moved entry, entry 1 = old entry 0
+    return sym;
+}
+
 // ---- encode v2: warp per chunk ------------------------------------------------------------
 constexpr int VSMAX = 288;           // virtual slots: sigma rounded up to a multiple of 32
 constexpr int ENC_WARPS = 8;         // warps (chunks) per CTA
@@ -583,9 +618,7 @@ __global__ void mtfd_perm_kernel(const uint16_t *__restrict__ idx, uint64_t N, u
             atomicMax(err, 1u);
             r = 0;
         }
-        uint16_t h = lst.get16(r);
-        for (int j = (int)r; j > 0; j--) lst.set16(j, lst.get16(j - 1));
-        lst.set16(0, h);
+        list_take16(lst, r);
     }
     for (int j = 0; j < (int)sigma; j++) perm[k * sigma + j] = lst.get16(j);
 }
@@ -814,10 +847,7 @@ __global__ void mtfd_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N,
     for (uint64_t i = beg; i < end; i++) {
         uint32_t r = idx[i];
         if (r >= sigma) r = 0;
-        uint16_t h = lst.get16(r);
-        for (int j = (int)r; j > 0; j--) lst.set16(j, lst.get16(j - 1));
-        lst.set16(0, h);
-        out[i] = (int16_t)h;
+        out[i] = (int16_t)list_take16(lst, r);
     }
 }
 
@@ -838,15 +868,6 @@ int mtf_read_final(tc_ctx *ctx, const uint16_t *d_final, uint32_t sigma, const i
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (uint32_t j = 0; j < sigma; j++) final_list[j] = alpha[h_final[j]];
     return TC_OK;
-}
-
-uint32_t pick_chunk_len(tc_ctx *ctx, uint64_t N, uint32_t lo, uint32_t hi) {
-    uint64_t target_threads = (uint64_t)ctx->sm_count * 128;
-    uint64_t L = ceil_div_u64(N, target_threads);
-    L = (L + 15) / 16 * 16;
-    if (L < lo) L = lo;
-    if (L > hi) L = hi;
-    return (uint32_t)L;
 }
 
 // present_hint (257 flags, code = symbol + 1, 0 = Nothing): the alphabet when the caller already
@@ -988,7 +1009,10 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
         tc_ws_release(ctx, mk);
         return h_err[0] ? TC_E_INDEX : TC_OK;
     }
-    const uint32_t L = pick_chunk_len(ctx, N, 64, 512);
+    // ~512 chunks per SM keep the 12 resident warps per SM (516 B of list per thread) busy
+    uint64_t Lw = ceil_div_u64(N, (uint64_t)ctx->sm_count * 512);
+    Lw = (Lw + 15) / 16 * 16;
+    const uint32_t L = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(Lw, 64), 512);
     const uint64_t nchunks = ceil_div_u64(N, L);
     const uint32_t G = 128;
     const uint64_t ntiles = ceil_div_u64(nchunks, G);
