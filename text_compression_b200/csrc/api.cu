@@ -427,15 +427,23 @@ extern "C" int tc_bwt_mtf_rle_decode(tc_ctx *ctx, const uint32_t *count, const i
     TC_TRY(ws_alloc(ctx, R, &d_rsym));
     TC_TRY(h2d(ctx, d_count, count, R));
     TC_TRY(h2d(ctx, d_rsym, rsym, R));
-    uint64_t N = 0;
-    int rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
-    if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    uint64_t N = info->N; // the caller's block header knows the BWT length: no sizing pass over the runs
+    int rc = TC_OK;
+    if (N == 0) {
+        rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
+        if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    }
     if (N == 0) return TC_OK;
     if (N >= 0xfffffffeull) return TC_E_TOOBIG;
     TC_TRY(ws_alloc(ctx, N, &d_idx));
     TC_TRY(ws_alloc(ctx, N, &d_sym));
     TC_TRY(ws_alloc(ctx, N, &d_text));
-    TC_TRY(rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_idx, N, &N)); // index stream: int16 == uint16 here
+    {
+        uint64_t Ngot = 0;
+        rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_idx, N, &Ngot); // index stream: int16 == uint16 here
+        if (rc != TC_OK && rc != TC_E_CAP) return rc;
+        if (Ngot != N) return TC_E_ARG; // the runs do not add up to the length the header states
+    }
     TC_TRY(mtf_decode_dev_impl(ctx, (const uint16_t *)d_idx, N, info->final_list, info->sigma, d_sym));
     rc = bwt_decode_i16_dev_impl(ctx, d_sym, N, d_text, N, n_out);
     if (rc != TC_OK) return rc;

@@ -835,14 +835,17 @@ __global__ void __launch_bounds__(32)
 // D3: replay with the real symbols.
 __global__ void mtfd_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t L, uint64_t nchunks,
                                    uint32_t G, uint32_t sigma, const uint16_t *__restrict__ part,
-                                   const int16_t *__restrict__ tileprefix, int16_t *__restrict__ out) {
+                                   const uint16_t *__restrict__ part2, const int16_t *__restrict__ superprefix,
+                                   int16_t *__restrict__ out) {
     extern __shared__ uint32_t smem[];
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nchunks) return;
     TState lst{smem};
-    const int16_t *tp = tileprefix + (k / G) * sigma;
+    // incoming list = (list at the super-tile start) . (tiles before this one) . (chunks before this one)
+    const int16_t *sp = superprefix + (k / G / G) * sigma;
+    const uint16_t *p2 = part2 + (k / G) * sigma;
     const uint16_t *pp = part + k * sigma;
-    for (int j = 0; j < (int)sigma; j++) lst.set16(j, (uint16_t)tp[pp[j]]);
+    for (int j = 0; j < (int)sigma; j++) lst.set16(j, (uint16_t)sp[p2[pp[j]]]);
     uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
     for (uint64_t i = beg; i < end; i++) {
         uint32_t r = idx[i];
@@ -1014,15 +1017,19 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
     Lw = (Lw + 15) / 16 * 16;
     const uint32_t L = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(Lw, 64), 512);
     const uint64_t nchunks = ceil_div_u64(N, L);
-    const uint32_t G = 128;
-    const uint64_t ntiles = ceil_div_u64(nchunks, G);
-    uint16_t *perm, *part, *tilesum;
-    int16_t *tileprefix;
+    // three levels of serial composition chains (64 chunks per tile, 64 tiles per super-tile, then
+    // the super-tiles): no chain is longer than 64 steps for blocks up to 64 MiB
+    const uint32_t G = 64;
+    const uint64_t ntiles = ceil_div_u64(nchunks, G), nsuper = ceil_div_u64(ntiles, G);
+    uint16_t *perm, *part, *tilesum, *part2, *supersum;
+    int16_t *superprefix;
     uint32_t *d_err;
     TC_TRY(ws_alloc(ctx, nchunks * sigma, &perm));
     TC_TRY(ws_alloc(ctx, nchunks * sigma, &part));
     TC_TRY(ws_alloc(ctx, ntiles * sigma, &tilesum));
-    TC_TRY(ws_alloc(ctx, ntiles * sigma, &tileprefix));
+    TC_TRY(ws_alloc(ctx, ntiles * sigma, &part2));
+    TC_TRY(ws_alloc(ctx, nsuper * sigma, &supersum));
+    TC_TRY(ws_alloc(ctx, nsuper * sigma, &superprefix));
     TC_TRY(ws_alloc(ctx, 1, &d_err));
     TC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream));
     const int T = 64;
@@ -1031,8 +1038,10 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
     TC_LAUNCH(ctx, mtfd_perm_kernel, cgrid, T, smem, d_idx, N, L, nchunks, sigma, perm, d_err);
     TC_LAUNCH(ctx, mtfd_tile_chain_kernel, (unsigned)ceil_div_u64(ntiles, 4), 128, 0, perm, nchunks, G, sigma, part,
               tilesum, ntiles);
-    TC_LAUNCH(ctx, mtfd_top_chain_kernel, 1, 32, 0, tilesum, ntiles, sigma, l0, tileprefix);
-    TC_LAUNCH(ctx, mtfd_replay_kernel, cgrid, T, smem, d_idx, N, L, nchunks, G, sigma, part, tileprefix, d_sym);
+    TC_LAUNCH(ctx, mtfd_tile_chain_kernel, (unsigned)ceil_div_u64(nsuper, 4), 128, 0, tilesum, ntiles, G, sigma, part2,
+              supersum, nsuper);
+    TC_LAUNCH(ctx, mtfd_top_chain_kernel, 1, 32, 0, supersum, nsuper, sigma, l0, superprefix);
+    TC_LAUNCH(ctx, mtfd_replay_kernel, cgrid, T, smem, d_idx, N, L, nchunks, G, sigma, part, part2, superprefix, d_sym);
     uint32_t *h_err = (uint32_t *)ctx->h_scal;
     TC_TRY(tc_d2h_small(ctx, h_err, d_err, sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
