@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(RT)
     }
 }
 
-// single block: exclusive sum of pairs (u64) and exclusive max of head / just over tiles
+// single block: exclusive sum of pairs (u64) and exclusive max of head / just over tiles.  Every
+// thread owns RS_PER consecutive tiles (local scan in registers), so 8 Ki tiles -- a 32 MiB index
+// stream -- need one round of three block scans.
+constexpr int RS_PER = 8;
 __global__ void __launch_bounds__(1024)
     rle_tile_scan_kernel(const uint32_t *__restrict__ tile_pairs, uint32_t *tile_head, uint32_t *tile_just,
                          uint64_t *__restrict__ tile_off, uint64_t tiles) {
@@ -131,20 +134,36 @@ __global__ void __launch_bounds__(1024)
     __shared__ uint32_t sh32[1024 / 32 + 1];
     uint64_t carry = 0;
     uint32_t ch = 0, cj = 0;
-    for (uint64_t b = 0; b < tiles; b += 1024) {
-        uint64_t t = b + threadIdx.x;
-        uint64_t v = t < tiles ? tile_pairs[t] : 0;
-        uint32_t h = t < tiles ? tile_head[t] : 0;
-        uint32_t j = t < tiles ? tile_just[t] : 0;
+    for (uint64_t b = 0; b < tiles; b += 1024 * RS_PER) {
+        const uint64_t t0 = b + (uint64_t)threadIdx.x * RS_PER;
+        uint32_t p[RS_PER], h[RS_PER], j[RS_PER];
+        uint64_t v = 0;
+        uint32_t hm = 0, jm = 0;
+#pragma unroll
+        for (int q = 0; q < RS_PER; q++) {
+            const bool in = t0 + q < tiles;
+            p[q] = in ? tile_pairs[t0 + q] : 0;
+            h[q] = in ? tile_head[t0 + q] : 0;
+            j[q] = in ? tile_just[t0 + q] : 0;
+            v += p[q];
+            hm = max(hm, h[q]);
+            jm = max(jm, j[q]);
+        }
         uint64_t tot;
         uint32_t th, tj;
-        uint64_t ex = block_excl_sum<uint64_t, 1024>(v, sh64, &tot);
-        uint32_t hx = block_excl_max<uint32_t, 1024>(h, 0u, sh32, &th);
-        uint32_t jx = block_excl_max<uint32_t, 1024>(j, 0u, sh32, &tj);
-        if (t < tiles) {
-            tile_off[t] = carry + ex;
-            tile_head[t] = max(ch, hx);
-            tile_just[t] = max(cj, jx);
+        uint64_t ex = carry + block_excl_sum<uint64_t, 1024>(v, sh64, &tot);
+        uint32_t hx = max(ch, block_excl_max<uint32_t, 1024>(hm, 0u, sh32, &th));
+        uint32_t jx = max(cj, block_excl_max<uint32_t, 1024>(jm, 0u, sh32, &tj));
+#pragma unroll
+        for (int q = 0; q < RS_PER; q++) {
+            if (t0 + q < tiles) {
+                tile_off[t0 + q] = ex;
+                tile_head[t0 + q] = hx;
+                tile_just[t0 + q] = jx;
+            }
+            ex += p[q];
+            hx = max(hx, h[q]);
+            jx = max(jx, j[q]);
         }
         carry += tot;
         ch = max(ch, th);
