@@ -2,7 +2,7 @@
 // (src/Data/BWT.hs:93-104 + sortTB / magicInverseBWT, src/Data/BWT/Internal.hs:144-200).
 //
 // Inverse: the reference sorts (symbol, index) pairs -- a stable counting
-// sort, done here as two 8-bit radix passes over a 9-bit code -- which yields psi, then walks
+// sort, done here in one pass over the 257 symbol codes (cs_* kernels) -- which yields psi, then walks
 //   f = psi[0]; while f != 0: emit F[f]; f = psi[f]
 // The walk is a linked list over rows; it is parallelised by list ranking with splitters:
 // every K-th row is a splitter, each splitter walks to the next splitter (sub-list length),
@@ -49,23 +49,121 @@ struct CodeI16 {
     }
 };
 
+// ---- psi by ONE stable counting pass over the 257 symbol codes ----------------------------------
+// (the generic radix sort needs two 8-bit passes over (key, value) pairs for a 9-bit code)
+//   cs_hist    per-tile code counts, code-major matrix hist[code * tiles + tile]
+//   cs_rows    exclusive scan of every code's row over tiles + row totals
+//   cs_base    exclusive scan of the 257 totals = first row of every code in F (the C table)
+//   cs_scatter stable rank inside the tile (warp match groups, warp-private counters), then
+//              psi[base[code] + offs[code][tile] + rank] = position
+constexpr int CS_T = 256;
+constexpr int CS_ITEMS = 16;
+constexpr int CS_TILE = CS_T * CS_ITEMS;
+constexpr int CS_WARPS = CS_T / 32;
+constexpr int CS_BINS = 288; // 257 codes, padded
+
 template <class Src>
-__global__ void __launch_bounds__(256)
-    inv_keys_kernel(Src src, uint64_t N, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
-                    uint32_t *__restrict__ hist /*257*/) {
-    __shared__ uint32_t h[257];
-    for (int j = threadIdx.x; j < 257; j += 256) h[j] = 0;
+__global__ void __launch_bounds__(CS_T)
+    cs_hist_kernel(Src src, uint64_t N, uint32_t *__restrict__ hist, uint64_t tiles) {
+    __shared__ uint32_t h[CS_WARPS][CS_BINS];
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    for (int j = threadIdx.x; j < CS_WARPS * CS_BINS; j += CS_T) (&h[0][0])[j] = 0;
     __syncthreads();
-    uint64_t stride = (uint64_t)gridDim.x * 256;
-    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < N; i += stride) {
-        uint32_t c = src.at(i);
-        keys[i] = c;
-        vals[i] = (uint32_t)i;
-        atomicAdd(&h[c], 1u);
+    const uint64_t wbase = (uint64_t)blockIdx.x * CS_TILE + (uint64_t)w * (32 * CS_ITEMS);
+#pragma unroll 4
+    for (int r = 0; r < CS_ITEMS; r++) {
+        const uint64_t i = wbase + (uint64_t)r * 32 + lane;
+        const bool valid = i < N;
+        const uint32_t c = valid ? src.at(i) : 0u;
+        const unsigned peers = match_bits<9>(c, valid);
+        if (valid && (peers & lanemask_lt()) == 0) h[w][c] += __popc(peers); // warp-private: no atomics
+        __syncwarp();
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < 257; j += 256)
-        if (h[j]) atomicAdd(&hist[j], h[j]);
+    for (int c = threadIdx.x; c < 257; c += CS_T) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int ww = 0; ww < CS_WARPS; ww++) s += h[ww][c];
+        hist[(uint64_t)c * tiles + blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+    cs_rows_kernel(uint32_t *__restrict__ hist, uint64_t tiles, uint32_t *__restrict__ totals) {
+    __shared__ uint32_t sh[1024 / 32 + 1];
+    uint32_t *row = hist + (uint64_t)blockIdx.x * tiles;
+    uint32_t carry = 0;
+    for (uint64_t b0 = 0; b0 < tiles; b0 += 1024) {
+        const uint64_t i = b0 + threadIdx.x;
+        const uint32_t v = i < tiles ? row[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = block_excl_sum<uint32_t, 1024>(v, sh, &tot);
+        if (i < tiles) row[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+// totals[0..257) -> exclusive scan in place (first F row per code) and a copy of the counts
+__global__ void __launch_bounds__(512) cs_base_kernel(uint32_t *totals, uint32_t *__restrict__ counts) {
+    __shared__ uint32_t sh[512 / 32 + 1];
+    const uint32_t v = threadIdx.x < 257 ? totals[threadIdx.x] : 0;
+    const uint32_t ex = block_excl_sum<uint32_t, 512>(v, sh, (uint32_t *)nullptr);
+    if (threadIdx.x < 257) {
+        totals[threadIdx.x] = ex;
+        counts[threadIdx.x] = v;
+    }
+}
+
+template <class Src>
+__global__ void __launch_bounds__(CS_T)
+    cs_scatter_kernel(Src src, uint64_t N, const uint32_t *__restrict__ offs, const uint32_t *__restrict__ base,
+                      uint64_t tiles, uint32_t *__restrict__ psi) {
+    __shared__ uint16_t wcount[CS_WARPS][CS_BINS];
+    __shared__ uint32_t gbase[CS_BINS];
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    for (int j = threadIdx.x; j < CS_WARPS * CS_BINS / 2; j += CS_T) reinterpret_cast<uint32_t *>(&wcount[0][0])[j] = 0;
+    __syncthreads();
+    const uint64_t wbase = (uint64_t)blockIdx.x * CS_TILE + (uint64_t)w * (32 * CS_ITEMS);
+    uint32_t code[CS_ITEMS / 2]; // two 16-bit codes per register
+    uint32_t rnk[CS_ITEMS / 2];  // two 16-bit ranks per register
+#pragma unroll
+    for (int r = 0; r < CS_ITEMS; r++) {
+        const uint64_t i = wbase + (uint64_t)r * 32 + lane;
+        const bool valid = i < N;
+        const uint32_t c = valid ? src.at(i) : 0u;
+        const unsigned peers = match_bits<9>(c, valid);
+        const uint32_t pre = valid ? wcount[w][c] : 0;
+        __syncwarp();
+        if (valid && (peers & lt) == 0) wcount[w][c] = (uint16_t)(pre + __popc(peers));
+        __syncwarp();
+        const uint32_t rk = pre + __popc(peers & lt);
+        code[r >> 1] = (r & 1) ? (code[r >> 1] | (c << 16)) : c;
+        rnk[r >> 1] = (r & 1) ? (rnk[r >> 1] | (rk << 16)) : rk;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 257; c += CS_T) { // exclusive prefix over the tile's warps + global row start
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < CS_WARPS; ww++) {
+            const uint32_t t = wcount[ww][c];
+            wcount[ww][c] = (uint16_t)run;
+            run += t;
+        }
+        gbase[c] = base[c] + offs[(uint64_t)c * tiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < CS_ITEMS; r++) {
+        const uint64_t i = wbase + (uint64_t)r * 32 + lane;
+        if (i < N) {
+            const uint32_t c = (code[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+            psi[gbase[c] + wcount[w][c] + ((rnk[r >> 1] >> (16 * (r & 1))) & 0xffffu)] = (uint32_t)i;
+        }
+    }
 }
 
 struct CStart {
@@ -147,18 +245,18 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
     if (N == 0) return TC_OK;
     if (N >= 0xfffffffeull) return TC_E_TOOBIG;
     WsMark mk = tc_ws_mark(ctx);
-    uint64_t *k0, *k1;
-    uint32_t *v0, *v1, *d_hist;
-    TC_TRY(ws_alloc(ctx, N, &k0));
-    TC_TRY(ws_alloc(ctx, N, &k1));
-    TC_TRY(ws_alloc(ctx, N, &v0));
-    TC_TRY(ws_alloc(ctx, N, &v1));
-    TC_TRY(ws_alloc(ctx, 260, &d_hist));
-    TC_CUDA(cudaMemsetAsync(d_hist, 0, 260 * sizeof(uint32_t), ctx->stream));
-    unsigned grid = (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256), (uint64_t)ctx->sm_count * 16);
-    TC_LAUNCH(ctx, (inv_keys_kernel<Src>), grid, 256, 0, src, N, k0, v0, d_hist);
+    // stable counting sort of the positions by symbol code == psi
+    const uint64_t tiles = ceil_div_u64(N, CS_TILE);
+    uint32_t *hist, *totals, *d_counts, *psi;
+    TC_TRY(ws_alloc(ctx, 257 * tiles, &hist));
+    TC_TRY(ws_alloc(ctx, 260, &totals));
+    TC_TRY(ws_alloc(ctx, 260, &d_counts));
+    TC_TRY(ws_alloc(ctx, N, &psi));
+    TC_LAUNCH(ctx, (cs_hist_kernel<Src>), (unsigned)tiles, CS_T, 0, src, N, hist, tiles);
+    TC_LAUNCH(ctx, cs_rows_kernel, 257, 1024, 0, hist, tiles, totals);
+    TC_LAUNCH(ctx, cs_base_kernel, 1, 512, 0, totals, d_counts);
     uint32_t *h = (uint32_t *)ctx->h_scal;
-    TC_TRY(tc_d2h_small(ctx, h, d_hist, 257 * sizeof(uint32_t)));
+    TC_TRY(tc_d2h_small(ctx, h, d_counts, 257 * sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h[0] == 0) { // no Nothing: empty result (src/Data/BWT/Internal.hs:174-175)
         tc_ws_release(ctx, mk);
@@ -171,24 +269,19 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
         acc += h[c];
     }
     cs.c[257] = acc;
-    // stable sort by code == psi
-    int shifts[2] = {0, 8};
-    uint64_t *ks;
-    uint32_t *psi;
-    TC_TRY(tc_radix_sort_pairs(ctx, k0, v0, k1, v1, N, shifts, 2, &ks, &psi));
+    ctx->prof_bytes_next = N * (sizeof(*src.p) + 4);
+    TC_LAUNCH(ctx, (cs_scatter_kernel<Src>), (unsigned)tiles, CS_T, 0, src, N, hist, totals, tiles, psi);
     // list ranking
     const uint32_t K = 32;
     const uint64_t S = ceil_div_u64(N, K);
-    uint32_t *nxtA = (uint32_t *)k0, *nxtB = nxtA + S, *dA = nxtB + S, *dB = dA + S; // keys are dead: 4S*4 <= 8N bytes
+    uint32_t *nxtA, *nxtB, *dA, *dB;
+    TC_TRY(ws_alloc(ctx, S, &nxtA));
+    TC_TRY(ws_alloc(ctx, S, &nxtB));
+    TC_TRY(ws_alloc(ctx, S, &dA));
+    TC_TRY(ws_alloc(ctx, S, &dB));
     uint32_t *d_err;
     TC_TRY(ws_alloc(ctx, 1, &d_err));
     TC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream));
-    if (ks == k0) { // two passes: the sorted pairs are back in buffer 0, so buffer 1 is the free one
-        nxtA = (uint32_t *)k1;
-        nxtB = nxtA + S;
-        dA = nxtB + S;
-        dB = dA + S;
-    }
     const unsigned gridS = (unsigned)ceil_div_u64(S, 128);
     TC_LAUNCH(ctx, inv_walk1_kernel, gridS, 128, 0, psi, S, K, N, nxtA, dA);
     int rounds = 1;
