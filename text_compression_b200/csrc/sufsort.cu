@@ -541,7 +541,7 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&v)[PER], unsigned lane) 
 
 // load the bucket (coalesced), sort it, leave the sorted words in we[0..M)
 template <int PER>
-__device__ __forceinline__ void fs_sort_bucket(const uint2 *__restrict__ rec, uint32_t M, int fsh, uint32_t fmask,
+__device__ __forceinline__ bool fs_sort_bucket(const uint2 *__restrict__ rec, uint32_t M, int fsh, uint32_t fmask,
                                                uint32_t *we, unsigned lane) {
     uint32_t v[PER];
 #pragma unroll
@@ -550,10 +550,17 @@ __device__ __forceinline__ void fs_sort_bucket(const uint2 *__restrict__ rec, ui
         v[r] = j < M ? ((((rec[j].x >> fsh) & fmask) << 9) | j) : 0xffffffffu;
     }
     warp_bitonic<PER>(v, lane);
+    // neighbours with equal field?  (padding words are all ones and never tie with a record)
+    bool tie = false;
+#pragma unroll
+    for (int r = 0; r + 1 < PER; r++) tie |= (v[r] >> 9) == (v[r + 1] >> 9) && lane * PER + r + 1 < M;
+    const uint32_t nxt = __shfl_down_sync(TC_FULL, v[0], 1);
+    tie |= lane < 31 && (v[PER - 1] >> 9) == (nxt >> 9) && (lane + 1) * PER < M;
 #pragma unroll
     for (int r = 0; r < PER; r++)
         if (lane * PER + r < M) we[lane * PER + r] = v[r];
     __syncwarp();
+    return __any_sync(TC_FULL, tie);
 }
 
 // Order of two suffixes whose first k symbols agree: compare the following keys, k symbols at
@@ -628,12 +635,12 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 5)
     const int fbits = rb < 23 ? rb : 23;
     const int fsh = rb - fbits;
     const uint32_t fmask = (fbits ? (0xffffffffu >> (32 - fbits)) : 0u);
-    if (M <= 256) fs_sort_bucket<8>(rec + s, M, fsh, fmask, W.e, lane);
-    else fs_sort_bucket<16>(rec + s, M, fsh, fmask, W.e, lane);
+    const bool any_tie = M <= 256 ? fs_sort_bucket<8>(rec + s, M, fsh, fmask, W.e, lane)
+                                  : fs_sort_bucket<16>(rec + s, M, fsh, fmask, W.e, lane);
     // runs of equal field (rare): the lane holding the head of a run sorts it by full keys
     bool head = false;
     uint32_t eqpairs = 0;
-    for (uint32_t j = lane; j + 1 < M; j += 32) {
+    for (uint32_t j = lane; any_tie && j + 1 < M; j += 32) {
         const uint32_t f = W.e[j] >> 9;
         const bool eq = (W.e[j + 1] >> 9) == f;
         eqpairs += eq;
