@@ -713,7 +713,7 @@ __global__ void sa_build_isa_kernel(const uint32_t *__restrict__ g, const uint32
 // sorted keys), so no inverse suffix array is needed yet
 __global__ void sa_keys2_lookup_kernel(const uint32_t *__restrict__ cj, uint64_t U, const uint32_t *__restrict__ sa,
                                        const uint64_t *__restrict__ keys, uint64_t N, const uint32_t *__restrict__ g,
-                                       uint64_t h, uint64_t n, const uint64_t *__restrict__ pw, int b, int kb,
+                                       uint64_t h, uint64_t n, const uint64_t *__restrict__ pw, int b, int kb, int gsh,
                                        uint64_t *__restrict__ key2, uint32_t *__restrict__ val2) {
     uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= U) return;
@@ -730,7 +730,7 @@ __global__ void sa_keys2_lookup_kernel(const uint32_t *__restrict__ cj, uint64_t
         }
         r2 = (uint32_t)lo;
     }
-    key2[m] = ((uint64_t)(g[j] - 1) << 32) | r2;
+    key2[m] = ((uint64_t)(g[j] - 1) << gsh) | r2; // group and rank packed tightly: fewer radix passes
     val2[m] = s;
 }
 
@@ -744,14 +744,14 @@ __global__ void sa_compact_kernel(const uint32_t *__restrict__ ns, const uint32_
 
 __global__ void sa_keys2_kernel(const uint32_t *__restrict__ cj, uint64_t U, const uint32_t *__restrict__ sa,
                                 const uint32_t *__restrict__ isa, const uint32_t *__restrict__ g, uint64_t h,
-                                uint64_t n, uint64_t *__restrict__ key2, uint32_t *__restrict__ val2) {
+                                uint64_t n, int gsh, uint64_t *__restrict__ key2, uint32_t *__restrict__ val2) {
     uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= U) return;
     uint32_t j = cj[m];
     uint32_t s = sa[j];
     uint64_t nx = (uint64_t)s + h;
     uint32_t r2 = nx <= n ? isa[nx] : 0u; // nx <= n always holds for unresolved suffixes
-    key2[m] = ((uint64_t)(g[j] - 1) << 32) | r2;
+    key2[m] = ((uint64_t)(g[j] - 1) << gsh) | r2; // group and rank packed tightly: fewer radix passes
     val2[m] = s;
 }
 
@@ -991,8 +991,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         const int rb = bits_for(N - 1);
         int sh2[16];
         int np2 = 0;
-        for (int s = 0; s < rb; s += 8) sh2[np2++] = s;
-        for (int s = 0; s < rb; s += 8) sh2[np2++] = 32 + s;
+        for (int s = 0; s < 2 * rb; s += 8) sh2[np2++] = s; // key = group << rb | rank: 2*rb bits
         uint64_t h = (uint64_t)k;
         for (int round = 0; U > 0; round++) {
             if (round > 48) {
@@ -1001,14 +1000,14 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
             }
             const unsigned gridU = (unsigned)ceil_div_u64(U, 256);
             if (round == 0) {
-                TC_LAUNCH(ctx, sa_keys2_lookup_kernel, gridU, 256, 0, cjA, U, d_sa, keys, N, g, h, n, pw, b, kb, key2a,
+                TC_LAUNCH(ctx, sa_keys2_lookup_kernel, gridU, 256, 0, cjA, U, d_sa, keys, N, g, h, n, pw, b, kb, rb, key2a,
                           val2a);
             } else {
                 if (!isa) { // second round: now the inverse suffix array pays for itself
                     TC_TRY(ws_alloc(ctx, N, &isa));
                     TC_LAUNCH(ctx, sa_build_isa_kernel, gridN, 256, 0, g, d_sa, N, isa);
                 }
-                TC_LAUNCH(ctx, sa_keys2_kernel, gridU, 256, 0, cjA, U, d_sa, isa, g, h, n, key2a, val2a);
+                TC_LAUNCH(ctx, sa_keys2_kernel, gridU, 256, 0, cjA, U, d_sa, isa, g, h, n, rb, key2a, val2a);
             }
             uint64_t *k2s;
             uint32_t *v2s;
