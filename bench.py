@@ -212,8 +212,13 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
-        for i in range(args.warmup):
+        # warm-up: at least W steps and at least a quarter of a second of work, so that every GPU of a
+        # multi-GPU run has left its idle clocks (210 MHz) before the timed region starts
+        t_w = time.perf_counter()
+        i = 0
+        while i < args.warmup or time.perf_counter() - t_w < 0.25:
             step_dev(i)
+            i += 1
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
@@ -228,6 +233,8 @@ def run_b200(args):
         sampler.stop_flag.set()
         sampler.join()
         ms = ev0.elapsed_time(ev1)
+        if os.environ.get("TC_BENCH_DEBUG"):
+            print(f"[rank {rank}] {ms / args.steps:.4f} ms/step", file=sys.stderr)
         R_last = int(info.R)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
