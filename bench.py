@@ -333,6 +333,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "block_bytes": n, "blocks_per_step": world, "sigma": int(info.sigma),
                        "runs_per_block": R_last,
+                       "warmup_note": "W untimed steps, extended to >= 0.25 s so all GPUs leave idle clocks",
                        "l2": f"inputs rotate over {NBLOCKS} distinct blocks ({NBLOCKS * n >> 20} MiB > L2); "
                              "each step streams > 1 GB of sort traffic"},
             "clocks": sampler.summary(),
