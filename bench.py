@@ -221,7 +221,8 @@ def run_b200(args):
             i += 1
         barrier()
         sampler = ClockSampler(local)
-        sampler.start()
+        if rank == 0:   # the line reports rank 0's clocks; NVML polling from every rank contends on the driver
+            sampler.start()
         launches0 = ctx.launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
@@ -231,7 +232,8 @@ def run_b200(args):
         barrier()
         launches = ctx.launches - launches0
         sampler.stop_flag.set()
-        sampler.join()
+        if rank == 0:
+            sampler.join()
         ms = ev0.elapsed_time(ev1)
         if os.environ.get("TC_BENCH_DEBUG"):
             print(f"[rank {rank}] {ms / args.steps:.4f} ms/step", file=sys.stderr)
