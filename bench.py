@@ -184,6 +184,8 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: text_compression_b200 has no CPU path")
     torch.cuda.set_device(local)
+    from text_compression_b200 import multi as _multi
+    numa_bound = _multi.bind_to_gpu_cpus(local)   # pinned buffers on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
@@ -342,7 +344,7 @@ def run_b200(args):
             "e2e": {"value": e2e_val, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
                     "api": "tc_blocks_encode: one call over `steps` blocks, pinned host buffers in and out, copies "
                            "of neighbouring blocks overlapped with compute",
-                    "single_block_call_MBps": e2e_single},
+                    "single_block_call_MBps": e2e_single, "cpu_affinity_bound_to_gpu": bool(numa_bound)},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "passes": passes,

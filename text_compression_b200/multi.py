@@ -24,6 +24,27 @@ def world():
     return 1, 0
 
 
+def bind_to_gpu_cpus(gpu_index: int) -> bool:
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity), so that pinned
+    host buffers are allocated on, and copied over, the GPU's own PCIe root / NUMA node.  One
+    process per GPU; call before allocating pinned memory.  Returns False if NVML is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def blocks_of_rank(n_blocks: int, world_size: int, rank: int):
     """Round-robin block assignment: block b belongs to rank b mod world."""
     return list(range(rank, n_blocks, world_size))
