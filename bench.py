@@ -10,8 +10,9 @@ N GPUs process N blocks per step with no data-path collective: weak scaling).
 
 Timed region of `value`: inputs already resident in HBM, CUDA events on the launching stream,
 barrier + synchronize on both sides, max over ranks.  `e2e` is the same metric through the
-host-buffer C-ABI call (tc_bwt_mtf_rle_encode) with H2D of the text and D2H of the runs inside
-the timed region.  Inputs rotate over 12 distinct blocks (192 MiB > the 126 MB L2) and every
+host-buffer C-ABI call (tc_blocks_encode_packed: text in pinned host memory in, packed block
+containers in pinned host memory out) with every block's H2D and D2H inside the timed region;
+the record-output call (tc_blocks_encode) and the single-block call are timed beside it.  Inputs rotate over 12 distinct blocks (192 MiB > the 126 MB L2) and every
 step streams ~4 GB through HBM, so nothing is L2-resident between steps.
 
 The reference is Haskell and no GHC exists in the image (probed on the GPU box too), so the
@@ -247,39 +248,58 @@ def run_b200(args):
         value = world * args.steps * n / 1e6 / (ms / 1e3)
 
         # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region.  The call is
-        # tc_blocks_encode, the multi-block entry point: one call compresses `steps` blocks from pinned
-        # host memory into pinned host memory, overlapping the copies of neighbouring blocks with
-        # the kernels of the current one (every block's H2D and D2H happen inside the call).
+        # tc_blocks_encode_packed, the multi-block entry point with container output: one call
+        # compresses `steps` blocks from pinned host memory into pinned host memory, overlapping the
+        # copies of neighbouring blocks with the kernels of the current one (every block's H2D and
+        # D2H happen inside the call).  The container carries the same runs at 2 bytes + 1 bit each
+        # (tc_packed_unpack gives the 6-byte records back); the record-output call tc_blocks_encode
+        # is timed beside it.
         NH = 4
+        pcap = int(ctx.L.tc_packed_bound(n))
         h_in = [_lib.pinned_empty(n, np.uint8) for _ in range(NH)]
+        h_out = [_lib.pinned_empty(pcap, np.uint8) for _ in range(NH)]
         h_cnt = [_lib.pinned_empty(cap, np.uint32) for _ in range(NH)]
         h_sym = [_lib.pinned_empty(cap, np.int16) for _ in range(NH)]
         for j in range(NH):
             h_in[j][:] = host_blocks[j]
 
-        def batch(nb):
+        def batch(nb, packed=True):
             tp = (C.c_void_p * nb)(*[h_in[b % NH].ctypes.data for b in range(nb)])
+            ns = (C.c_uint64 * nb)(*([n] * nb))
+            infos = (BlockInfo * nb)()
+            if packed:
+                op = (C.c_void_p * nb)(*[h_out[b % NH].ctypes.data for b in range(nb)])
+                caps = (C.c_uint64 * nb)(*([pcap] * nb))
+                nbytes = (C.c_uint64 * nb)()
+                ctx.call("tc_blocks_encode_packed", nb, tp, ns, 1, op, caps, nbytes, infos)
+                return infos, int(nbytes[nb - 1])
             cp = (C.c_void_p * nb)(*[h_cnt[b % NH].ctypes.data for b in range(nb)])
             sp = (C.c_void_p * nb)(*[h_sym[b % NH].ctypes.data for b in range(nb)])
-            ns = (C.c_uint64 * nb)(*([n] * nb))
             caps = (C.c_uint64 * nb)(*([cap] * nb))
-            infos = (BlockInfo * nb)()
             ctx.call("tc_blocks_encode", nb, tp, ns, 1, cp, sp, caps, infos)
-            return infos
+            return infos, int(infos[nb - 1].R) * 6
 
-        batch(max(3, min(args.warmup, 4)))
-        barrier()
+        def timed_batch(packed):
+            batch(max(3, min(args.warmup, 4)), packed)
+            barrier()
+            t0 = time.perf_counter()
+            _, nbytes = batch(args.steps, packed)
+            torch.cuda.synchronize()
+            e_s = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([e_s], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e_s = float(t.item())
+            return world * args.steps * n / 1e6 / e_s, nbytes
+
         e_steps = args.steps
-        t0 = time.perf_counter()
-        einfos = batch(e_steps)
-        torch.cuda.synchronize()
-        e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e_s], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_s = float(t.item())
-        e2e_val = world * e_steps * n / 1e6 / e_s
-        d2h = int(einfos[e_steps - 1].R) * 6
+        e2e_records, d2h_records = timed_batch(False)
+        e2e_val, d2h = timed_batch(True)
+        # the container of the last block must unpack to runs that cover its BWT
+        last = h_out[(e_steps - 1) % NH]
+        uinfo = BlockInfo()
+        assert ctx.L.tc_packed_unpack(ptr(last), d2h, ptr(h_cnt[0]), ptr(h_sym[0]), cap, C.byref(uinfo)) == 0
+        assert int(h_cnt[0][: int(uinfo.R)].sum(dtype=np.uint64)) == n + 1 and d2h_records == 6 * int(uinfo.R)
         # the single-block call (tc_bwt_mtf_rle_encode), copies not overlapped, for comparison
         sinfo = BlockInfo()
         ctx.call("tc_bwt_mtf_rle_encode", ptr(h_in[0]), n, ptr(h_cnt[0]), ptr(h_sym[0]), cap, C.byref(sinfo))
@@ -342,8 +362,10 @@ def run_b200(args):
                              "each step streams > 1 GB of sort traffic"},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_val, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
-                    "api": "tc_blocks_encode: one call over `steps` blocks, pinned host buffers in and out, copies "
-                           "of neighbouring blocks overlapped with compute",
+                    "api": "tc_blocks_encode_packed: one call over `steps` blocks, pinned host buffers in and out, "
+                           "copies of neighbouring blocks overlapped with compute; output = packed block container "
+                           "(header + runs at 2 B + 1 bit each, lossless: tc_packed_unpack returns the records)",
+                    "record_output_MBps": e2e_records, "record_output_d2h_bytes_per_step": d2h_records,
                     "single_block_call_MBps": e2e_single, "cpu_affinity_bound_to_gpu": bool(numa_bound)},
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -132,6 +132,46 @@ int tc_bwt_mtf_rle_encode(tc_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t
  * batch has been processed (info[b].R tells the size needed). */
 int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n, int with_mtf,
                      uint32_t *const *count, int16_t *const *rsym, const uint64_t *cap, tc_block_info *info);
+/* ---- packed block container (the reference has only Show/Read,
+ * src/Data/RLE/Internal.hs:95-96, src/Data/MTF/Internal.hs:67-68) --------------------
+ * One compressed block as a single little-endian byte string: the tc_block_info fields, then the
+ * runs at 2 bytes + 1 bit each instead of the 6-byte (count, symbol) record, so a stream of blocks
+ * moves a third of the bytes over PCIe:
+ *   cnt8[R]   min(count, 255)
+ *   sym8[R]   low byte of the symbol's 9-bit code (code = symbol & 0x1ff: MTF indices 0..256 as
+ *             they are, BWT symbols 0..255 as they are, Nothing = 0x1ff)
+ *   hi[ceil(R/32)] u32 words, bit k%32 of word k/32 = bit 8 of run k's code
+ *   big_idx[n_big] u64, big_cnt[n_big] u32: the runs whose count is >= 255, ascending run index
+ * Sections start at the 16-byte-aligned offsets the header states.  The container is lossless for
+ * the run sequence: tc_packed_unpack gives back exactly what tc_blocks_encode returns. */
+#define TC_PACKED_MAGIC 0x314b4c4242434254ull /* "TCBBLK1" */
+#define TC_PACKED_MTF 1u                      /* flags bit 0: runs are over the MTF index stream */
+typedef struct {
+    uint64_t magic;
+    uint32_t version; /* 1 */
+    uint32_t flags;
+    uint64_t n, N, primary, R, n_big, total_bytes;
+    uint64_t off_cnt8, off_sym8, off_hi, off_big_idx, off_big_cnt; /* from the start of the container */
+    uint32_t sigma;
+    uint32_t reserved;
+    int16_t final_list[257];
+    int16_t pad[7];
+} tc_packed_header; /* 640 bytes */
+/* Upper bound of the container size for a block of n text bytes. */
+uint64_t tc_packed_bound(uint64_t n);
+/* tc_blocks_encode with container output: out[b] receives cap[b] >= tc_packed_bound(n[b]) bytes at
+ * most, out_bytes[b] the size written.  Same pipelining; the packing runs on the device right
+ * behind the RLE kernels. */
+int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n, int with_mtf,
+                            uint8_t *const *out, const uint64_t *cap, uint64_t *out_bytes, tc_block_info *info);
+/* Host-only (no device, no context): header check + tc_block_info of a container. */
+int tc_packed_info(const void *blob, uint64_t bytes, tc_block_info *info, uint32_t *flags);
+/* Host-only: container -> the run records of tc_blocks_encode.  R > cap gives TC_E_CAP (info->R set). */
+int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *count, int16_t *rsym, uint64_t cap,
+                     tc_block_info *info);
+/* Container -> text on the device (unpack kernel, then the inverse chain below). */
+int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap, uint64_t *n_out);
+
 /* inverses: runs -> (MTF indices ->) BWT -> text. */
 int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
                       uint64_t cap, uint64_t *n_out);

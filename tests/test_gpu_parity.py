@@ -289,6 +289,11 @@ def test_block_over_16mib_roundtrip(ctx):
     blk = block.compress_bwt_mtf_rle(text, ctx)
     assert blk.N == text.size + 1 and int(blk.counts.sum()) == blk.N
     assert block.decompress(blk, ctx) == text.tobytes()
+    blob = block.compress_blocks_packed([text], True, ctx)[0]
+    u = block.unpack_block(blob)
+    assert np.array_equal(u.counts, blk.counts) and np.array_equal(u.syms, blk.syms)
+    assert u.final_list.tolist() == blk.final_list.tolist() and blob.size < 2.2 * text.size
+    assert block.decompress_packed(blob, ctx) == text.tobytes()
     blk2 = block.compress_bwt_rle(gen_acgtn(0xC6, 16 << 20), ctx)
     assert block.decompress(blk2, ctx) == gen_acgtn(0xC6, 16 << 20).tobytes()
 
@@ -412,6 +417,40 @@ def test_compress_blocks_pipeline(ctx, orc):
     assert g0.counts.tolist() == cnt.tolist() and g0.syms.tolist() == sym.tolist()
 
 
+def test_packed_container(ctx, orc):
+    """tc_blocks_encode_packed writes, byte for byte, the container an independent numpy writer lays
+    out from the ORACLE's runs (long runs -> count exceptions in run order, Nothing symbols, MTF
+    index 256, ragged and empty blocks); host unpack and device decode invert it."""
+    from tests.util import pack_container
+    from text_compression_b200 import block
+    texts = [gen_acgtn(1, 70001), gen_bytes(2, 4096), np.empty(0, np.uint8), gen_ascii(3, 33333), gen_acgt(4, 5),
+             np.frombuffer(b"a" * 300000 + b"b" * 255 + b"c" * 254 + b"ab" * 4000 + b"z" * 70000, np.uint8),
+             np.tile(np.arange(256, dtype=np.uint8), 40), np.repeat(gen_bytes(8, 600), 700), gen_bytes(5, 200000),
+             gen_acgtn(6, 1)]
+    for with_mtf in (True, False):
+        got = block.compress_blocks_packed(texts, with_mtf, ctx)
+        assert len(got) == len(texts)
+        for t, blob in zip(texts, got):
+            if t.size == 0:
+                want = pack_container(0, 0, 0, 0, [], [], [], with_mtf)
+            else:
+                bwt = orc.bwt_encode(t)
+                primary = int(np.nonzero(bwt < 0)[0][0])
+                if with_mtf:
+                    idx, fin = orc.mtf_encode(bwt)
+                    cnt, sym = orc.rle_encode(idx.astype(np.int16))
+                else:
+                    fin = np.empty(0, np.int16)
+                    cnt, sym = orc.rle_encode(bwt)
+                want = pack_container(t.size, t.size + 1, primary, len(fin), fin, cnt, sym, with_mtf)
+            assert blob.size == want.size and np.array_equal(blob, want), (t.size, with_mtf)
+            u = block.unpack_block(blob)
+            if t.size:
+                assert np.array_equal(u.counts, cnt) and np.array_equal(u.syms, sym)
+            if with_mtf or u.primary != u.N - 1 or t.size == 0:   # Q1: the reference's own round trip breaks there
+                assert block.decompress_packed(blob, ctx) == t.tobytes()
+
+
 def test_q1_trailing_nothing_stream(ctx, orc):
     """Texts that are their own greatest suffix: the reference's RLE re-emits a stale pair (Q1)
     and its own round trip breaks; the GPU stream must equal the oracle's, not round-trip."""
@@ -430,3 +469,8 @@ def test_block_16mib_roundtrip(ctx):
     assert blk.N == text.size + 1 and int(blk.counts.sum()) == blk.N      # run lengths cover the BWT
     assert sorted(blk.final_list.tolist()) == [-1] + list(range(256))
     assert block.decompress(blk, ctx) == text.tobytes()
+    blob = block.compress_blocks_packed([text], True, ctx)[0]
+    u = block.unpack_block(blob)
+    assert np.array_equal(u.counts, blk.counts) and np.array_equal(u.syms, blk.syms)
+    assert u.final_list.tolist() == blk.final_list.tolist() and blob.size < 2.2 * text.size
+    assert block.decompress_packed(blob, ctx) == text.tobytes()

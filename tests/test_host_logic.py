@@ -93,3 +93,46 @@ def test_generators_are_deterministic():
     assert set(np.unique(t).tolist()) <= set(b"ACGTN") and 500 < int((t == ord("N")).sum()) < 1500
     r = gen_reads(1, gen_acgt(2, 5000), 100, 20)
     assert r.shape == (100, 20)
+
+
+def test_packed_container_host_side():
+    """The packed block container (include/tc_b200.h): tc_packed_unpack / tc_packed_info are host-only
+    and must read what an independent numpy writer (tests/util.pack_container) lays out from the
+    ORACLE's runs -- long runs (count >= 255 exceptions), Nothing symbols, MTF index 256."""
+    import ctypes as C
+    from oracle import oracle
+    from tests.util import gen_acgtn, gen_bytes, pack_container
+    from text_compression_b200 import _lib, block
+    L = _lib.load()
+    texts = [gen_acgtn(7, 5000), np.frombuffer(b"a" * 3000 + b"b" * 255 + b"c" * 254 + b"ab" * 40, np.uint8),
+             np.tile(np.arange(256, dtype=np.uint8), 5), gen_bytes(9, 3000), np.frombuffer(b"x", np.uint8)]
+    for t in texts:
+        bwt = oracle.bwt_encode(t)
+        primary = int(np.nonzero(bwt < 0)[0][0])
+        for with_mtf in (False, True):
+            if with_mtf:
+                idx, fin = oracle.mtf_encode(bwt)
+                cnt, sym = oracle.rle_encode(idx.astype(np.int16))
+            else:
+                fin = np.empty(0, np.int16)
+                cnt, sym = oracle.rle_encode(bwt)
+            blob = pack_container(t.size, t.size + 1, primary, len(fin), fin, cnt, sym, with_mtf)
+            assert blob.size <= L.tc_packed_bound(t.size)
+            got = block.unpack_block(blob)
+            assert (got.n, got.N, got.primary, got.sigma, got.with_mtf) == (t.size, t.size + 1, primary, len(fin), with_mtf)
+            assert got.final_list.tolist() == fin.tolist()
+            assert np.array_equal(got.counts, cnt) and np.array_equal(got.syms, sym)
+    assert (cnt >= 0).all() and any((oracle.rle_encode(oracle.bwt_encode(texts[1]))[0] >= 255).tolist())
+    assert 256 in oracle.mtf_encode(oracle.bwt_encode(texts[2]))[0].tolist()
+    # malformed containers are refused, never read out of bounds
+    info = _lib.BlockInfo()
+    bad = blob.copy(); bad[0] ^= 1
+    assert L.tc_packed_info(_lib.ptr(bad), bad.size, C.byref(info), None) == _lib.TC_E_ARG
+    assert L.tc_packed_info(_lib.ptr(blob), blob.size - 1, C.byref(info), None) == _lib.TC_E_ARG
+    assert L.tc_packed_info(_lib.ptr(blob), 100, C.byref(info), None) == _lib.TC_E_ARG
+    bad = blob.copy(); bad[40:48] = np.frombuffer(np.uint64(1 << 40).tobytes(), np.uint8)   # R
+    assert L.tc_packed_info(_lib.ptr(bad), bad.size, C.byref(info), None) == _lib.TC_E_ARG
+    cnt1 = np.empty(1, np.uint32); sym1 = np.empty(1, np.int16)
+    blob2 = pack_container(3, 4, 0, 0, [], [1, 2, 1], [5, 6, -1], False)
+    assert L.tc_packed_unpack(_lib.ptr(blob2), blob2.size, _lib.ptr(cnt1), _lib.ptr(sym1), 1, C.byref(info)) == _lib.TC_E_CAP
+    assert info.R == 3

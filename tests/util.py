@@ -40,3 +40,36 @@ def gen_reads(seed, text, q, m, mut_frac=0.10):
     rows = np.nonzero(mut)[0]
     reads[rows, pos[rows]] = sub[rows]
     return reads
+
+
+def pack_container(n, N, primary, sigma, final_list, counts, syms, with_mtf) -> np.ndarray:
+    """Independent numpy writer of the packed block container (include/tc_b200.h, tc_packed_header):
+    what tc_blocks_encode_packed must produce byte for byte from the oracle's runs."""
+    import struct
+    counts = np.asarray(counts, dtype=np.uint32)
+    syms = np.asarray(syms, dtype=np.int16)
+    R = int(counts.size)
+    big = np.nonzero(counts >= 255)[0].astype(np.uint64)
+    al = lambda x: (x + 15) & ~15
+    off_cnt8 = 640
+    off_sym8 = al(off_cnt8 + R)
+    off_hi = al(off_sym8 + R)
+    off_big_idx = al(off_hi + (R + 31) // 32 * 4)
+    off_big_cnt = al(off_big_idx + 8 * big.size)
+    total = al(off_big_cnt + 4 * big.size)
+    out = np.zeros(total, dtype=np.uint8)
+    fl = np.zeros(257 + 7, dtype=np.int16)
+    fl[: len(final_list)] = np.asarray(final_list, dtype=np.int16)
+    hdr = struct.pack("<QII6Q5QII", 0x314B4C4242434254, 1, 1 if with_mtf else 0, n, N, primary, R, int(big.size), total,
+                      off_cnt8, off_sym8, off_hi, off_big_idx, off_big_cnt, sigma, 0) + fl.tobytes()
+    assert len(hdr) == 640
+    out[:640] = np.frombuffer(hdr, dtype=np.uint8)
+    code = syms.astype(np.int32) & 0x1FF
+    out[off_cnt8:off_cnt8 + R] = np.minimum(counts, 255).astype(np.uint8)
+    out[off_sym8:off_sym8 + R] = (code & 0xFF).astype(np.uint8)
+    bits = np.zeros((R + 31) // 32 * 32, dtype=np.uint8)
+    bits[:R] = code >> 8
+    out[off_hi:off_hi + bits.size // 8] = np.packbits(bits, bitorder="little")
+    out[off_big_idx:off_big_idx + 8 * big.size] = big.view(np.uint8)
+    out[off_big_cnt:off_big_cnt + 4 * big.size] = counts[big.astype(np.int64)].view(np.uint8)
+    return out

@@ -77,6 +77,11 @@ _SIGS = {
     "tc_bwt_rle_encode": (_int, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(BlockInfo)]),
     "tc_bwt_mtf_rle_encode": (_int, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(BlockInfo)]),
     "tc_blocks_encode": (_int, [_vp, _u64, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(BlockInfo)]),
+    "tc_packed_bound": (_u64, [_u64]),
+    "tc_blocks_encode_packed": (_int, [_vp, _u64, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(BlockInfo)]),
+    "tc_packed_info": (_int, [_vp, _u64, C.POINTER(BlockInfo), _pu32]),
+    "tc_packed_unpack": (_int, [_vp, _u64, _vp, _vp, _u64, C.POINTER(BlockInfo)]),
+    "tc_packed_decode": (_int, [_vp, _vp, _u64, _vp, _u64, _pu64]),
     "tc_bwt_rle_decode": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _pu64]),
     "tc_bwt_mtf_rle_decode": (_int, [_vp, _vp, _vp, C.POINTER(BlockInfo), _vp, _u64, _pu64]),
     "tc_bwt_encode_dev": (_int, [_vp, _vp, _u64, _vp, _pu64, _vp]),

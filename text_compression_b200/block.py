@@ -4,6 +4,10 @@
   compress_bwt_mtf_rle  = bytestringToBWTToMTFB, then seqToRLE over the index stream
                           (the "BWT+MTF+RLE" composite of BASELINE.json)
 BWT -> MTF -> RLE never leaves HBM; only the text goes in and the runs come out.
+
+Packed block container (layout in include/tc_b200.h): compress_blocks_packed
+returns each block as one byte string (header + runs at 2 bytes + 1 bit each); unpack_block turns
+it back into the run records on the host, decompress_packed into the text on the device.
 """
 from __future__ import annotations
 
@@ -12,7 +16,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import TC_E_CAP, BlockInfo, default_context, ptr
+from ._lib import TC_E_CAP, TC_OK, BlockInfo, _raise, default_context, load, ptr
 from .seq import to_bytes
 
 
@@ -104,4 +108,61 @@ def decompress(blk: CompressedBlock, ctx=None) -> bytes:
         ctx.call("tc_bwt_mtf_rle_decode", ptr(cnt), ptr(sym), C.byref(info), ptr(out), cap, C.byref(n_out))
     else:
         ctx.call("tc_bwt_rle_decode", ptr(cnt), ptr(sym), blk.R, ptr(out), cap, C.byref(n_out))
+    return out[: n_out.value].tobytes()
+
+
+def compress_blocks_packed(texts, with_mtf: bool = True, ctx=None, pinned: bool = True) -> list:
+    """tc_blocks_encode_packed: one container (uint8 array) per input block, in input order."""
+    from ._lib import pinned_empty
+    ctx = ctx or default_context()
+    ts = [np.ascontiguousarray(t if isinstance(t, np.ndarray) else np.frombuffer(to_bytes(t), dtype=np.uint8),
+                               dtype=np.uint8) for t in texts]
+    nb = len(ts)
+    if nb == 0:
+        return []
+    alloc = pinned_empty if pinned else (lambda k, dt: np.empty(k, dtype=dt))
+    bound = [int(ctx.L.tc_packed_bound(t.size)) for t in ts]
+    outs = [alloc(b, np.uint8) for b in bound]
+    ns = (C.c_uint64 * nb)(*[t.size for t in ts])
+    caps = (C.c_uint64 * nb)(*bound)
+    nbytes = (C.c_uint64 * nb)()
+    tp = (C.c_void_p * nb)(*[t.ctypes.data for t in ts])
+    op = (C.c_void_p * nb)(*[o.ctypes.data for o in outs])
+    infos = (BlockInfo * nb)()
+    ctx.call("tc_blocks_encode_packed", nb, tp, ns, 1 if with_mtf else 0, op, caps, nbytes, infos)
+    return [outs[b][: int(nbytes[b])].copy() for b in range(nb)]
+
+
+def unpack_block(blob) -> CompressedBlock:
+    """tc_packed_unpack (host only, no device): container -> CompressedBlock with the run records."""
+    L = load()
+    a = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob)
+    info = BlockInfo()
+    flags = C.c_uint32(0)
+    rc = L.tc_packed_info(ptr(a), a.size, C.byref(info), C.byref(flags))
+    if rc != TC_OK:
+        _raise(None, rc)
+    R = int(info.R)
+    cnt = np.empty(R, dtype=np.uint32)
+    sym = np.empty(R, dtype=np.int16)
+    rc = L.tc_packed_unpack(ptr(a), a.size, ptr(cnt), ptr(sym), R, C.byref(info))
+    if rc != TC_OK:
+        _raise(None, rc)
+    fin = np.array(info.final_list[: info.sigma], dtype=np.int16)
+    return CompressedBlock(int(info.n), int(info.N), int(info.primary), int(info.sigma), fin, cnt, sym,
+                           bool(flags.value & 1))
+
+
+def decompress_packed(blob, ctx=None) -> bytes:
+    """tc_packed_decode: container -> text (unpacked and decoded on the device)."""
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob)
+    info = BlockInfo()
+    rc = ctx.L.tc_packed_info(ptr(a), a.size, C.byref(info), None)
+    if rc != TC_OK:
+        _raise(None, rc)
+    cap = int(info.n) + 2
+    out = np.empty(cap, dtype=np.uint8)
+    n_out = C.c_uint64(0)
+    ctx.call("tc_packed_decode", ptr(a), a.size, ptr(out), cap, C.byref(n_out))
     return out[: n_out.value].tobytes()

@@ -255,7 +255,7 @@ void info_clear(tc_block_info *info, uint64_t n) {
 
 // text (device) -> BWT -> [MTF ->] RLE, everything stays in HBM.
 int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, uint32_t *d_count, int16_t *d_rsym,
-                 uint64_t cap, tc_block_info *info) {
+                 uint64_t cap, tc_block_info *info, RlePack *pk = nullptr) {
     info_clear(info, n);
     if (n == 0) return TC_OK;
     const uint64_t N = n + 1;
@@ -263,7 +263,7 @@ int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, 
     TC_TRY(ws_alloc(ctx, N, &d_bwt));
     TC_TRY(bwt_encode_dev_impl(ctx, d_text, n, d_bwt, &info->primary, nullptr));
     info->N = N;
-    if (!with_mtf) return rle_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_count, d_rsym, cap, &info->R);
+    if (!with_mtf) return rle_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_count, d_rsym, cap, &info->R, pk);
     uint16_t *d_idx;
     TC_TRY(ws_alloc(ctx, N, &d_idx));
     // alphabet of the BWT = the text's bytes (histogram kept by the suffix sort) + the sentinel
@@ -271,7 +271,7 @@ int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, 
     present[0] = 1;
     for (int c = 0; c < 256; c++) present[c + 1] = ctx->text_hist[c] != 0;
     TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma, present));
-    int rc = rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R); // syncs the stream
+    int rc = rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R, pk); // syncs the stream
     int rc2 = mtf_finish_pending(ctx);
     return rc != TC_OK ? rc : rc2;
 }
@@ -317,6 +317,21 @@ extern "C" int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uin
     return compress_dev(ctx, d_text, n, true, d_count, d_rsym, cap, info);
 }
 
+namespace {
+// copy streams + events of the batch entry points (created on first use)
+int blocks_streams(tc_ctx *ctx) {
+    if (ctx->s_h2d) return TC_OK;
+    TC_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    TC_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+    }
+    TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp, cudaEventDisableTiming));
+    return TC_OK;
+}
+} // namespace
+
 // Pipelined batch: slot = b & 1.  H2D of block b+1 is issued before block b is compressed, the
 // D2H of block b right after it (compress_dev returns with the stream drained, so the host
 // knows R); compressing block b+2 into the same slot first waits for that D2H.
@@ -331,15 +346,7 @@ extern "C" int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *co
         if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
         nmax = n[b] > nmax ? n[b] : nmax;
     }
-    if (!ctx->s_h2d) {
-        TC_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-        TC_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-            TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
-        }
-        TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp, cudaEventDisableTiming));
-    }
+    TC_TRY(blocks_streams(ctx));
     const uint64_t worst = nmax + 3;
     uint8_t *d_text[2];
     uint32_t *d_count[2];
@@ -383,34 +390,55 @@ extern "C" int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *co
     return rc_all;
 }
 
-extern "C" int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
-                                 uint64_t cap, uint64_t *n_out) {
-    TC_ENTER(ctx);
-    if (!n_out) return TC_E_ARG;
-    *n_out = 0;
-    if (R == 0) return TC_OK;
-    // N is not known up front: a first pass sizes it (TC_E_CAP with cap 0 returns the length)
-    uint32_t *d_count;
-    int16_t *d_rsym, *d_sym;
-    uint8_t *d_text;
-    TC_TRY(ws_alloc(ctx, R, &d_count));
-    TC_TRY(ws_alloc(ctx, R, &d_rsym));
-    TC_TRY(h2d(ctx, d_count, count, R));
-    TC_TRY(h2d(ctx, d_rsym, rsym, R));
-    uint64_t N = 0;
-    int rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
-    if (rc != TC_OK && rc != TC_E_CAP) return rc;
+namespace {
+// runs (device) -> [MTF indices ->] BWT -> text (host).  N == 0: sized by a first pass over the runs.
+int decode_runs_dev(tc_ctx *ctx, const uint32_t *d_count, const int16_t *d_rsym, uint64_t R, bool with_mtf,
+                    const tc_block_info *info, uint8_t *text, uint64_t cap, uint64_t *n_out) {
+    uint64_t N = with_mtf ? info->N : 0; // a block header knows the BWT length: no sizing pass over the runs
+    int rc = TC_OK;
+    if (N == 0) { // TC_E_CAP with cap 0 returns the length
+        rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
+        if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    }
     if (N == 0) return TC_OK;
     if (N >= 0xfffffffeull) return TC_E_TOOBIG;
-    TC_TRY(ws_alloc(ctx, N, &d_sym));
+    int16_t *d_a, *d_sym;
+    uint8_t *d_text;
+    TC_TRY(ws_alloc(ctx, N, &d_a));
     TC_TRY(ws_alloc(ctx, N, &d_text));
-    TC_TRY(rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_sym, N, &N));
+    {
+        uint64_t Ngot = 0;
+        rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_a, N, &Ngot);
+        if (rc != TC_OK && rc != TC_E_CAP) return rc;
+        if (Ngot != N) return TC_E_ARG; // the runs do not add up to the length the header states
+    }
+    d_sym = d_a;
+    if (with_mtf) { // index stream: int16 == uint16 here
+        TC_TRY(ws_alloc(ctx, N, &d_sym));
+        TC_TRY(mtf_decode_dev_impl(ctx, (const uint16_t *)d_a, N, info->final_list, info->sigma, d_sym));
+    }
     rc = bwt_decode_i16_dev_impl(ctx, d_sym, N, d_text, N, n_out);
     if (rc != TC_OK) return rc;
     uint64_t m = *n_out < cap ? *n_out : cap;
     TC_TRY(d2h(ctx, text, d_text, m));
     TC_TRY(sync(ctx));
     return *n_out > cap ? TC_E_CAP : TC_OK;
+}
+} // namespace
+
+extern "C" int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,
+                                 uint64_t cap, uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out) return TC_E_ARG;
+    *n_out = 0;
+    if (R == 0) return TC_OK;
+    uint32_t *d_count;
+    int16_t *d_rsym;
+    TC_TRY(ws_alloc(ctx, R, &d_count));
+    TC_TRY(ws_alloc(ctx, R, &d_rsym));
+    TC_TRY(h2d(ctx, d_count, count, R));
+    TC_TRY(h2d(ctx, d_rsym, rsym, R));
+    return decode_runs_dev(ctx, d_count, d_rsym, R, false, nullptr, text, cap, n_out);
 }
 
 extern "C" int tc_bwt_mtf_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym,
@@ -421,34 +449,193 @@ extern "C" int tc_bwt_mtf_rle_decode(tc_ctx *ctx, const uint32_t *count, const i
     const uint64_t R = info->R;
     if (R == 0) return TC_OK;
     uint32_t *d_count;
-    int16_t *d_rsym, *d_idx, *d_sym;
-    uint8_t *d_text;
+    int16_t *d_rsym;
     TC_TRY(ws_alloc(ctx, R, &d_count));
     TC_TRY(ws_alloc(ctx, R, &d_rsym));
     TC_TRY(h2d(ctx, d_count, count, R));
     TC_TRY(h2d(ctx, d_rsym, rsym, R));
-    uint64_t N = info->N; // the caller's block header knows the BWT length: no sizing pass over the runs
-    int rc = TC_OK;
-    if (N == 0) {
-        rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, nullptr, 0, &N);
-        if (rc != TC_OK && rc != TC_E_CAP) return rc;
+    return decode_runs_dev(ctx, d_count, d_rsym, R, true, info, text, cap, n_out);
+}
+
+// ---- packed block container (include/tc_b200.h; payload layout in rle.cu) -----------------------
+static_assert(sizeof(tc_packed_header) == 640, "tc_packed_header layout");
+namespace {
+inline uint64_t al16(uint64_t x) { return (x + 15) & ~15ull; }
+inline uint64_t big_cap_for(uint64_t n) { return (n + 1) / 255 + 4; }
+// section offsets for R runs and n_big exceptions; returns the container size
+uint64_t packed_layout(uint64_t R, uint64_t n_big, tc_packed_header *h) {
+    uint64_t o = sizeof(tc_packed_header);
+    h->off_cnt8 = o, o = al16(o + R);
+    h->off_sym8 = o, o = al16(o + R);
+    h->off_hi = o, o = al16(o + (R + 31) / 32 * 4);
+    h->off_big_idx = o, o = al16(o + n_big * 8);
+    h->off_big_cnt = o, o = al16(o + n_big * 4);
+    return h->total_bytes = o;
+}
+int packed_check(const void *blob, uint64_t bytes, tc_packed_header *h) {
+    if (!blob || bytes < sizeof *h) return TC_E_ARG;
+    memcpy(h, blob, sizeof *h);
+    if (h->magic != TC_PACKED_MAGIC || h->version != 1 || h->total_bytes > bytes || h->sigma > 257) return TC_E_ARG;
+    if (h->R > 0xffffffffull || h->n_big > h->R) return TC_E_ARG;
+    tc_packed_header want;
+    if (packed_layout(h->R, h->n_big, &want) != h->total_bytes || want.off_cnt8 != h->off_cnt8 ||
+        want.off_sym8 != h->off_sym8 || want.off_hi != h->off_hi || want.off_big_idx != h->off_big_idx ||
+        want.off_big_cnt != h->off_big_cnt)
+        return TC_E_ARG;
+    return TC_OK;
+}
+void packed_to_info(const tc_packed_header &h, tc_block_info *info) {
+    memset(info, 0, sizeof *info);
+    info->n = h.n, info->N = h.N, info->primary = h.primary, info->sigma = h.sigma, info->R = h.R;
+    memcpy(info->final_list, h.final_list, sizeof info->final_list);
+}
+} // namespace
+
+extern "C" uint64_t tc_packed_bound(uint64_t n) {
+    tc_packed_header h;
+    return packed_layout(n + 3, big_cap_for(n), &h);
+}
+
+extern "C" int tc_packed_info(const void *blob, uint64_t bytes, tc_block_info *info, uint32_t *flags) {
+    tc_packed_header h;
+    TC_TRY(packed_check(blob, bytes, &h));
+    if (info) packed_to_info(h, info);
+    if (flags) *flags = h.flags;
+    return TC_OK;
+}
+
+extern "C" int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *count, int16_t *rsym, uint64_t cap,
+                                tc_block_info *info) {
+    tc_packed_header h;
+    TC_TRY(packed_check(blob, bytes, &h));
+    if (info) packed_to_info(h, info);
+    if (h.R > cap) return TC_E_CAP;
+    if (h.R && (!count || !rsym)) return TC_E_ARG;
+    const uint8_t *base = (const uint8_t *)blob;
+    const uint8_t *c8 = base + h.off_cnt8, *s8 = base + h.off_sym8;
+    for (uint64_t k = 0; k < h.R; k++) {
+        uint32_t w;
+        memcpy(&w, base + h.off_hi + (k >> 5) * 4, 4);
+        const uint32_t code = s8[k] | (((w >> (k & 31)) & 1u) << 8);
+        count[k] = c8[k];
+        rsym[k] = code == 0x1ffu ? (int16_t)-1 : (int16_t)code;
     }
-    if (N == 0) return TC_OK;
-    if (N >= 0xfffffffeull) return TC_E_TOOBIG;
-    TC_TRY(ws_alloc(ctx, N, &d_idx));
-    TC_TRY(ws_alloc(ctx, N, &d_sym));
-    TC_TRY(ws_alloc(ctx, N, &d_text));
-    {
-        uint64_t Ngot = 0;
-        rc = rle_decode_dev_impl(ctx, d_count, d_rsym, R, d_idx, N, &Ngot); // index stream: int16 == uint16 here
-        if (rc != TC_OK && rc != TC_E_CAP) return rc;
-        if (Ngot != N) return TC_E_ARG; // the runs do not add up to the length the header states
+    uint64_t prev = 0;
+    for (uint64_t j = 0; j < h.n_big; j++) {
+        uint64_t idx;
+        uint32_t c;
+        memcpy(&idx, base + h.off_big_idx + j * 8, 8);
+        memcpy(&c, base + h.off_big_cnt + j * 4, 4);
+        if (idx >= h.R || (j && idx <= prev) || c < 255 || c8[idx] != 255) return TC_E_ARG;
+        count[idx] = c;
+        prev = idx;
     }
-    TC_TRY(mtf_decode_dev_impl(ctx, (const uint16_t *)d_idx, N, info->final_list, info->sigma, d_sym));
-    rc = bwt_decode_i16_dev_impl(ctx, d_sym, N, d_text, N, n_out);
-    if (rc != TC_OK) return rc;
-    uint64_t m = *n_out < cap ? *n_out : cap;
-    TC_TRY(d2h(ctx, text, d_text, m));
-    TC_TRY(sync(ctx));
-    return *n_out > cap ? TC_E_CAP : TC_OK;
+    return TC_OK;
+}
+
+extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n,
+                                       int with_mtf, uint8_t *const *out, const uint64_t *cap, uint64_t *out_bytes,
+                                       tc_block_info *info) {
+    TC_ENTER(ctx);
+    if (nblocks == 0) return TC_OK;
+    if (!text || !n || !out || !cap || !out_bytes || !info) return TC_E_ARG;
+    uint64_t nmax = 0;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+        nmax = n[b] > nmax ? n[b] : nmax;
+        out_bytes[b] = 0;
+    }
+    TC_TRY(blocks_streams(ctx));
+    const uint64_t worst = nmax + 3;
+    uint8_t *d_text[2];
+    RlePack pk[2];
+    uint32_t *d_count; // the 6-byte records never leave the device: one scratch copy serves both slots
+    int16_t *d_rsym;
+    TC_TRY(ws_alloc(ctx, worst, &d_count));
+    TC_TRY(ws_alloc(ctx, worst, &d_rsym));
+    for (int s = 0; s < 2; s++) {
+        TC_TRY(ws_alloc(ctx, nmax ? nmax : 1, &d_text[s]));
+        TC_TRY(ws_alloc(ctx, al16(worst), &pk[s].cnt8));
+        TC_TRY(ws_alloc(ctx, al16(worst), &pk[s].sym8));
+        TC_TRY(ws_alloc(ctx, (worst + 31) / 32, &pk[s].hi));
+        pk[s].big_cap = big_cap_for(nmax);
+        TC_TRY(ws_alloc(ctx, pk[s].big_cap, &pk[s].big_idx));
+        TC_TRY(ws_alloc(ctx, pk[s].big_cap, &pk[s].big_cnt));
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    bool d2h_pending[2] = {false, false};
+    int rc_all = TC_OK;
+    auto issue_h2d = [&](uint64_t b) -> int {
+        const int s = (int)(b & 1);
+        if (n[b]) TC_CUDA(cudaMemcpyAsync(d_text[s], text[b], n[b], cudaMemcpyHostToDevice, ctx->s_h2d));
+        TC_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d));
+        return TC_OK;
+    };
+    TC_TRY(issue_h2d(0));
+    for (uint64_t b = 0; b < nblocks; b++) {
+        const int s = (int)(b & 1);
+        if (b + 1 < nblocks) TC_TRY(issue_h2d(b + 1));
+        TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
+        if (d2h_pending[s]) TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));
+        WsMark mk = tc_ws_mark(ctx);
+        int rc = compress_dev(ctx, d_text[s], n[b], with_mtf != 0, d_count, d_rsym, worst, &info[b], &pk[s]);
+        tc_ws_release(ctx, mk);
+        if (rc != TC_OK) return rc;
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_packed_header h;
+        memset(&h, 0, sizeof h);
+        h.magic = TC_PACKED_MAGIC, h.version = 1, h.flags = with_mtf ? TC_PACKED_MTF : 0;
+        h.n = info[b].n, h.N = info[b].N, h.primary = info[b].primary, h.R = info[b].R, h.sigma = info[b].sigma;
+        h.n_big = n[b] ? pk[s].n_big : 0;
+        memcpy(h.final_list, info[b].final_list, sizeof h.final_list);
+        out_bytes[b] = packed_layout(h.R, h.n_big, &h);
+        if (out_bytes[b] > cap[b]) {
+            rc_all = TC_E_CAP;
+            continue;
+        }
+        uint8_t *o = out[b];
+        memcpy(o, &h, sizeof h);
+        // every section is copied at its exact length and its tail up to the next section is
+        // zeroed on the host, so every byte of the container is defined
+        auto section = [&](uint64_t off, const void *d_src, uint64_t len, uint64_t next) -> int {
+            if (len) TC_CUDA(cudaMemcpyAsync(o + off, d_src, len, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            memset(o + off + len, 0, next - off - len);
+            return TC_OK;
+        };
+        TC_TRY(section(h.off_cnt8, pk[s].cnt8, h.R, h.off_sym8));
+        TC_TRY(section(h.off_sym8, pk[s].sym8, h.R, h.off_hi));
+        TC_TRY(section(h.off_hi, pk[s].hi, (h.R + 31) / 32 * 4, h.off_big_idx));
+        TC_TRY(section(h.off_big_idx, pk[s].big_idx, h.n_big * 8, h.off_big_cnt));
+        TC_TRY(section(h.off_big_cnt, pk[s].big_cnt, h.n_big * 4, h.total_bytes));
+        TC_CUDA(cudaEventRecord(ctx->ev_d2h[s], ctx->s_d2h));
+        d2h_pending[s] = true;
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+    return rc_all;
+}
+
+extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap,
+                                uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out) return TC_E_ARG;
+    *n_out = 0;
+    tc_packed_header h;
+    TC_TRY(packed_check(blob, bytes, &h));
+    if (h.R == 0) return TC_OK;
+    tc_block_info info;
+    packed_to_info(h, &info);
+    const uint8_t *base = (const uint8_t *)blob;
+    uint8_t *d_blob; // payload sections keep their 16-byte alignment on the device
+    uint32_t *d_count;
+    int16_t *d_rsym;
+    const uint64_t pay = h.total_bytes - h.off_cnt8;
+    TC_TRY(ws_alloc(ctx, pay, &d_blob));
+    TC_TRY(ws_alloc(ctx, h.R, &d_count));
+    TC_TRY(ws_alloc(ctx, h.R, &d_rsym));
+    TC_TRY(h2d(ctx, d_blob, base + h.off_cnt8, pay));
+    const uint64_t o0 = h.off_cnt8;
+    TC_TRY(rle_unpack_dev_impl(ctx, d_blob, d_blob + (h.off_sym8 - o0), (const uint32_t *)(d_blob + (h.off_hi - o0)),
+                               (const uint64_t *)(d_blob + (h.off_big_idx - o0)),
+                               (const uint32_t *)(d_blob + (h.off_big_cnt - o0)), h.n_big, h.R, d_count, d_rsym));
+    return decode_runs_dev(ctx, d_count, d_rsym, h.R, (h.flags & TC_PACKED_MTF) != 0, &info, text, cap, n_out);
 }

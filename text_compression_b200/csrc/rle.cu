@@ -321,8 +321,104 @@ __global__ void __launch_bounds__(RT)
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;
 }
 
+
+// ---- packed run payload (block container) ------------------------------------
+// Runs leave the device as 2 bytes + 1 bit each instead of the 6-byte record:
+//   cnt8[k] = min(count, 255); sym8[k] = low byte of the symbol; hi bit k = bit 8 of the
+//   symbol's 9-bit code (set for MTF index 256 and for Nothing, whose code is 0x1ff);
+//   counts >= 255 are listed as (run index, count) exceptions, appended in arbitrary order here
+//   and sorted by run index before they leave the device.
+// One lane packs 8 consecutive runs: 48 B in (coalesced 128-bit loads), 17 B out.
+constexpr int PK_T = 256;
+__global__ void __launch_bounds__(PK_T)
+    rle_pack_kernel(const uint32_t *__restrict__ count, const int16_t *__restrict__ rsym,
+                    const uint64_t *__restrict__ d_R, uint64_t cap, uint2 *__restrict__ cnt8, uint2 *__restrict__ sym8,
+                    uint32_t *__restrict__ hi, uint64_t *__restrict__ big_idx, uint32_t *__restrict__ big_cnt,
+                    uint64_t big_cap, unsigned long long *__restrict__ n_big) {
+    const uint64_t R = min(*d_R, cap);
+    const uint64_t g = (uint64_t)blockIdx.x * PK_T + threadIdx.x; // group of 8 runs
+    const uint64_t k0 = g * 8;
+    if ((uint64_t)blockIdx.x * PK_T * 8 >= R) return; // whole CTA past the end
+    uint32_t c[8];
+    uint32_t s[8];
+    if (k0 + 8 <= R) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(count + k0);
+        const uint4 b = *reinterpret_cast<const uint4 *>(count + k0 + 4);
+        const uint4 v = *reinterpret_cast<const uint4 *>(rsym + k0);
+        c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = (w[k >> 1] >> ((k & 1) * 16)) & 0x1ffu;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool in = k0 + k < R;
+            c[k] = in ? count[k0 + k] : 0u;
+            s[k] = in ? ((uint32_t)(uint16_t)rsym[k0 + k] & 0x1ffu) : 0u;
+        }
+    }
+    uint32_t cw[2] = {0, 0}, sw[2] = {0, 0}, hb = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (c[k] >= 255u) {
+            const unsigned long long slot = atomicAdd(n_big, 1ull);
+            if (slot < big_cap) {
+                big_idx[slot] = k0 + k;
+                big_cnt[slot] = c[k];
+            }
+        }
+        cw[k >> 2] |= min(c[k], 255u) << ((k & 3) * 8);
+        sw[k >> 2] |= (s[k] & 0xffu) << ((k & 3) * 8);
+        hb |= (s[k] >> 8) << k;
+    }
+    // four lanes share one 32-bit word of the hi plane
+    hb <<= 8 * (threadIdx.x & 3);
+    hb |= __shfl_xor_sync(TC_FULL, hb, 1);
+    hb |= __shfl_xor_sync(TC_FULL, hb, 2);
+    if (k0 < R) {
+        cnt8[g] = make_uint2(cw[0], cw[1]);
+        sym8[g] = make_uint2(sw[0], sw[1]);
+    }
+    if ((threadIdx.x & 3) == 0 && k0 < R) hi[g >> 2] = hb;
+}
+
+// inverse of the packing for the device-side decoder: one thread per run; exceptions patched after
+__global__ void rle_unpack_kernel(const uint8_t *__restrict__ cnt8, const uint8_t *__restrict__ sym8,
+                                  const uint32_t *__restrict__ hi, uint64_t R, uint32_t *__restrict__ count,
+                                  int16_t *__restrict__ rsym) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= R) return;
+    const uint32_t code = sym8[k] | (((hi[k >> 5] >> (k & 31)) & 1u) << 8);
+    count[k] = cnt8[k];
+    rsym[k] = code == 0x1ffu ? (int16_t)-1 : (int16_t)code;
+}
+__global__ void rle_unpack_big_kernel(const uint64_t *__restrict__ big_idx, const uint32_t *__restrict__ big_cnt,
+                                      uint64_t n_big, uint64_t R, uint32_t *__restrict__ count) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_big && big_idx[j] < R) count[big_idx[j]] = big_cnt[j];
+}
+
+// exceptions in run order: LSD radix sort of (run index, count) on the 32 index bits
+int rle_sort_big(tc_ctx *ctx, RlePack *pk) {
+    WsMark mk = tc_ws_mark(ctx);
+    uint64_t *k1, *ko;
+    uint32_t *v1, *vo;
+    TC_TRY(ws_alloc(ctx, pk->n_big, &k1));
+    TC_TRY(ws_alloc(ctx, pk->n_big, &v1));
+    static const int shifts[4] = {0, 8, 16, 24};
+    TC_TRY(tc_radix_sort_pairs(ctx, pk->big_idx, pk->big_cnt, k1, v1, pk->n_big, shifts, 4, &ko, &vo));
+    if (ko != pk->big_idx) {
+        TC_CUDA(cudaMemcpyAsync(pk->big_idx, ko, pk->n_big * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        TC_CUDA(cudaMemcpyAsync(pk->big_cnt, vo, pk->n_big * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    tc_ws_release(ctx, mk);
+    return TC_OK;
+}
+
 template <class In>
-int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *d_rsym, uint64_t cap, uint64_t *R) {
+int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *d_rsym, uint64_t cap, uint64_t *R,
+                    RlePack *pk = nullptr) {
     *R = 0;
     if (N == 0) return TC_OK;
     if (N >= 0xfffffffeull) return TC_E_TOOBIG;
@@ -335,16 +431,32 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
     TC_TRY(ws_alloc(ctx, tiles, &th));
     TC_TRY(ws_alloc(ctx, tiles, &tj));
     TC_TRY(ws_alloc(ctx, tiles, &toff));
-    TC_TRY(ws_alloc(ctx, 1, &d_R));
+    TC_TRY(ws_alloc(ctx, 2, &d_R));
     TC_LAUNCH(ctx, (rle_reduce_kernel<In>), (unsigned)tiles, RT, 0, in, N, tp, th, tj);
     // NB: the reduce kernel's tile pair counts exclude the final flush; the emit kernel adds it
     // for the owner of position N-1, which is always in the last tile, so offsets stay exact.
     TC_LAUNCH(ctx, rle_tile_scan_kernel, 1, 1024, 0, tp, th, tj, toff, tiles);
     TC_LAUNCH(ctx, (rle_emit_kernel<In>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap, d_R);
-    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, sizeof(uint64_t)));
+    if (pk) {
+        // d_R and the exception counter sit next to each other so that one small copy brings both
+        // back; the pack grid covers the capacity and CTAs past R leave at once, so no host
+        // sync separates the emit kernel from the packing.
+        pk->n_big = 0;
+        TC_CUDA(cudaMemsetAsync(d_R + 1, 0, sizeof(uint64_t), ctx->stream));
+        const uint64_t groups = ceil_div_u64(cap, 8);
+        TC_LAUNCH(ctx, rle_pack_kernel, (unsigned)ceil_div_u64(groups, PK_T), PK_T, 0, d_count, d_rsym, d_R, cap,
+                  (uint2 *)pk->cnt8, (uint2 *)pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap,
+                  (unsigned long long *)(d_R + 1));
+    }
+    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, (pk ? 2 : 1) * sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     *R = ctx->h_scal[0];
     tc_ws_release(ctx, mk);
+    if (pk) {
+        pk->n_big = ctx->h_scal[1];
+        if (pk->n_big > pk->big_cap) return TC_E_CAP;
+        if (pk->n_big > 1) TC_TRY(rle_sort_big(ctx, pk));
+    }
     return *R > cap ? TC_E_CAP : TC_OK;
 }
 
@@ -428,13 +540,23 @@ int rle_decode_dev_impl(tc_ctx *ctx, const uint32_t *d_count, const int16_t *d_r
 }
 
 int rle_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint32_t *d_count,
-                           int16_t *d_rsym, uint64_t cap, uint64_t *R) {
+                           int16_t *d_rsym, uint64_t cap, uint64_t *R, RlePack *pk) {
     if (N && primary >= N) primary = ~0ull; // no Nothing in range: plain byte stream
-    return rle_encode_impl(ctx, InU8{d_bwt, primary}, N, d_count, d_rsym, cap, R);
+    return rle_encode_impl(ctx, InU8{d_bwt, primary}, N, d_count, d_rsym, cap, R, pk);
 }
 int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
-                            uint64_t cap, uint64_t *R) {
-    return rle_encode_impl(ctx, In16<false>{d_idx}, N, d_count, d_rsym, cap, R);
+                            uint64_t cap, uint64_t *R, RlePack *pk) {
+    return rle_encode_impl(ctx, In16<false>{d_idx}, N, d_count, d_rsym, cap, R, pk);
+}
+int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt8, const uint8_t *d_sym8, const uint32_t *d_hi,
+                        const uint64_t *d_big_idx, const uint32_t *d_big_cnt, uint64_t n_big, uint64_t R,
+                        uint32_t *d_count, int16_t *d_rsym) {
+    if (R == 0) return TC_OK;
+    TC_LAUNCH(ctx, rle_unpack_kernel, (unsigned)ceil_div_u64(R, 256), 256, 0, d_cnt8, d_sym8, d_hi, R, d_count, d_rsym);
+    if (n_big)
+        TC_LAUNCH(ctx, rle_unpack_big_kernel, (unsigned)ceil_div_u64(n_big, 256), 256, 0, d_big_idx, d_big_cnt, n_big, R,
+                  d_count);
+    return TC_OK;
 }
 int rle_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
                                uint64_t cap, uint64_t *R) {
