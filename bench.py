@@ -363,7 +363,8 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_val, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
                     "api": "tc_blocks_encode_packed: one call over `steps` blocks, pinned host buffers in and out, "
-                           "copies of neighbouring blocks overlapped with compute; output = packed block container "
+                           "copies of neighbouring blocks overlapped with compute, two blocks in flight (two lanes: contexts + "
+                           "host threads inside the call); output = packed block container "
                            "(header + runs at 2 B + 1 bit each, lossless: tc_packed_unpack returns the records)",
                     "record_output_MBps": e2e_records, "record_output_d2h_bytes_per_step": d2h_records,
                     "single_block_call_MBps": e2e_single, "cpu_affinity_bound_to_gpu": bool(numa_bound)},

@@ -2,6 +2,8 @@
 // composed helpers.  Host entry points stage through the scratch arena (H2D, kernels, D2H on
 // the context's stream); `_dev` entry points work on device pointers.  Every entry point
 // resets the arena exactly once; the *_impl functions never do.
+#include <thread>
+
 #include "common.cuh"
 #include "impl.cuh"
 
@@ -533,18 +535,13 @@ extern "C" int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *coun
     return TC_OK;
 }
 
-extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n,
-                                       int with_mtf, uint8_t *const *out, const uint64_t *cap, uint64_t *out_bytes,
-                                       tc_block_info *info) {
-    TC_ENTER(ctx);
-    if (nblocks == 0) return TC_OK;
-    if (!text || !n || !out || !cap || !out_bytes || !info) return TC_E_ARG;
-    uint64_t nmax = 0;
-    for (uint64_t b = 0; b < nblocks; b++) {
-        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
-        nmax = n[b] > nmax ? n[b] : nmax;
-        out_bytes[b] = 0;
-    }
+namespace {
+// One lane of the packed batch: blocks first, first + stride, ... through one context (its stream,
+// its two copy streams, double buffers: slot = k & 1 for the lane's k-th block).
+int blocks_packed_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nblocks, uint64_t nmax,
+                       const uint8_t *const *text, const uint64_t *n, int with_mtf, uint8_t *const *out,
+                       const uint64_t *cap, uint64_t *out_bytes, tc_block_info *info) {
+    TC_TRY(tc_ws_reset(ctx));
     TC_TRY(blocks_streams(ctx));
     const uint64_t worst = nmax + 3;
     uint8_t *d_text[2];
@@ -566,15 +563,15 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
     bool d2h_pending[2] = {false, false};
     int rc_all = TC_OK;
     auto issue_h2d = [&](uint64_t b) -> int {
-        const int s = (int)(b & 1);
+        const int s = (int)(((b - first) / stride) & 1);
         if (n[b]) TC_CUDA(cudaMemcpyAsync(d_text[s], text[b], n[b], cudaMemcpyHostToDevice, ctx->s_h2d));
         TC_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d));
         return TC_OK;
     };
-    TC_TRY(issue_h2d(0));
-    for (uint64_t b = 0; b < nblocks; b++) {
-        const int s = (int)(b & 1);
-        if (b + 1 < nblocks) TC_TRY(issue_h2d(b + 1));
+    TC_TRY(issue_h2d(first));
+    for (uint64_t b = first; b < nblocks; b += stride) {
+        const int s = (int)(((b - first) / stride) & 1);
+        if (b + stride < nblocks) TC_TRY(issue_h2d(b + stride));
         TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
         if (d2h_pending[s]) TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));
         WsMark mk = tc_ws_mark(ctx);
@@ -612,6 +609,42 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
     }
     TC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
     return rc_all;
+}
+} // namespace
+
+// Two lanes by default (TC_B200_LANES): even blocks on the caller's context and thread, odd blocks
+// on a child context driven by a helper thread.  Each block's kernel chain has short serial phases
+// (single-CTA scans, two host syncs); with two blocks in flight the other lane's kernels fill them.
+extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n,
+                                       int with_mtf, uint8_t *const *out, const uint64_t *cap, uint64_t *out_bytes,
+                                       tc_block_info *info) {
+    if (!ctx) return TC_E_ARG;
+    if (nblocks == 0) return TC_OK;
+    if (!text || !n || !out || !cap || !out_bytes || !info) return TC_E_ARG;
+    uint64_t nmax = 0;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+        nmax = n[b] > nmax ? n[b] : nmax;
+        out_bytes[b] = 0;
+    }
+    const bool two = ctx->lanes >= 2 && nblocks >= 2 && !ctx->prof_on;
+    if (two && !ctx->child) {
+        int rc = tc_ctx_create(ctx->device, &ctx->child);
+        if (rc != TC_OK) return rc;
+    }
+    if (!two) return blocks_packed_lane(ctx, 0, 1, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
+    int rc1 = TC_OK;
+    std::thread helper([&] {
+        rc1 = blocks_packed_lane(ctx->child, 1, 2, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
+    });
+    int rc0 = blocks_packed_lane(ctx, 0, 2, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
+    helper.join();
+    if (rc1 != TC_OK && rc1 != TC_E_CAP) {
+        memcpy(ctx->err, ctx->child->err, sizeof ctx->err);
+        return rc1;
+    }
+    if (rc0 != TC_OK) return rc0;
+    return rc1;
 }
 
 extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap,

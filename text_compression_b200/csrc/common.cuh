@@ -28,6 +28,7 @@ struct tc_ctx {
         size_t cap;
     };
     std::vector<Chunk> chunks;
+    size_t cur_chunk = 0; // cursor: chunk index and offset inside it
     size_t cur_off = 0;
     size_t used_total = 0;
     // pinned scalars for small device->host results
@@ -41,6 +42,10 @@ struct tc_ctx {
         int16_t *final_list = nullptr;
     } mtf_pending;
     uint32_t text_hist[256] = {0}; // byte histogram of the last text handed to the suffix sort
+    // second lane of the packed batch entry point (tc_blocks_encode_packed): a full context of its
+    // own on the same device, driven by a helper thread; created on first use
+    tc_ctx *child = nullptr;
+    int lanes = 2; // TC_B200_LANES=1: one block in flight
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     char err[512] = {0};
     // optional per-kernel timing (tc_ctx_profile): one event pair per launch
@@ -92,9 +97,8 @@ struct tc_ctx {
     TC_LAUNCH_AS(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 // ---- arena -------------------------------------------------------------------
-// ws_reset(): called at the start of a top-level op.  If the previous op spilled
-// into extra chunks, coalesce them into one chunk big enough for everything, so
-// steady state does no cudaMalloc.
+// ws_reset(): called at the start of a top-level op; moves the cursor back to the first chunk
+// (chunks are kept, see ctx.cu), so steady state does no cudaMalloc.
 int tc_ws_reset(tc_ctx *ctx);
 int tc_ws_alloc(tc_ctx *ctx, size_t bytes, void **out);
 template <typename T>
@@ -106,7 +110,7 @@ static inline int ws_alloc(tc_ctx *ctx, size_t count, T **out) {
 }
 // nested ops use mark/release so a composite can reuse scratch between stages
 struct WsMark {
-    size_t nchunks, off, used;
+    size_t nchunks, off, used; // nchunks = cursor chunk index at mark time
 };
 WsMark tc_ws_mark(tc_ctx *ctx);
 void tc_ws_release(tc_ctx *ctx, WsMark m);

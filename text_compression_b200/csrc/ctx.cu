@@ -23,7 +23,9 @@ extern "C" const char *tc_strerror(int rc) {
 }
 
 extern "C" const char *tc_last_error(const tc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
-extern "C" uint64_t tc_ctx_launches(const tc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t tc_ctx_launches(const tc_ctx *ctx) {
+    return ctx ? ctx->launches + (ctx->child ? ctx->child->launches : 0) : 0;
+}
 
 static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc_ctx **out) {
     if (!out) return TC_E_ARG;
@@ -42,6 +44,8 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     ctx->sm_count = prop.multiProcessorCount;
     const char *nm = getenv("TC_B200_NO_MSD");
     ctx->no_msd = nm && nm[0] == '1';
+    const char *ln = getenv("TC_B200_LANES");
+    if (ln && ln[0] >= '1' && ln[0] <= '2') ctx->lanes = ln[0] - '0';
     if (have_stream) {
         ctx->stream = stream;
         ctx->own_stream = false;
@@ -68,6 +72,7 @@ extern "C" int tc_ctx_create_on_stream(int device, void *cuda_stream, tc_ctx **o
 
 extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->child) tc_ctx_destroy(ctx->child);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &c : ctx->chunks) cudaFree(c.p);
@@ -151,22 +156,14 @@ extern "C" void tc_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+// The arena is a list of device chunks walked by a cursor (cur_chunk, cur_off).  A request that
+// does not fit the current chunk moves on to the next chunk that can hold it, and only when none
+// can is a new chunk allocated; reset and release just move the cursor back.  A repeated
+// allocation sequence (block after block of the same size) therefore reaches a steady state
+// after its first pass and never calls cudaMalloc again.
 int tc_ws_reset(tc_ctx *ctx) {
     TC_CUDA(cudaSetDevice(ctx->device));
-    if (ctx->chunks.size() > 1) {
-        size_t total = 0;
-        for (auto &c : ctx->chunks) total += c.cap;
-        TC_CUDA(cudaStreamSynchronize(ctx->stream));
-        for (auto &c : ctx->chunks) cudaFree(c.p);
-        ctx->chunks.clear();
-        char *p = nullptr;
-        total += total / 8;
-        if (cudaMalloc((void **)&p, total) != cudaSuccess) {
-            cudaGetLastError();
-            return TC_E_NOMEM;
-        }
-        ctx->chunks.push_back({p, total});
-    }
+    ctx->cur_chunk = 0;
     ctx->cur_off = 0;
     ctx->used_total = 0;
     return TC_OK;
@@ -175,7 +172,11 @@ int tc_ws_reset(tc_ctx *ctx) {
 int tc_ws_alloc(tc_ctx *ctx, size_t bytes, void **out) {
     bytes = (bytes + kAlign - 1) / kAlign * kAlign;
     if (bytes == 0) bytes = kAlign;
-    if (ctx->chunks.empty() || ctx->cur_off + bytes > ctx->chunks.back().cap) {
+    while (ctx->cur_chunk < ctx->chunks.size() && ctx->cur_off + bytes > ctx->chunks[ctx->cur_chunk].cap) {
+        ctx->cur_chunk++;
+        ctx->cur_off = 0;
+    }
+    if (ctx->cur_chunk >= ctx->chunks.size()) {
         size_t cap = bytes > (size_t(64) << 20) ? bytes : (size_t(64) << 20);
         char *p = nullptr;
         if (cudaMalloc((void **)&p, cap) != cudaSuccess) {
@@ -184,22 +185,20 @@ int tc_ws_alloc(tc_ctx *ctx, size_t bytes, void **out) {
             return TC_E_NOMEM;
         }
         ctx->chunks.push_back({p, cap});
+        ctx->cur_chunk = ctx->chunks.size() - 1;
         ctx->cur_off = 0;
     }
-    *out = ctx->chunks.back().p + ctx->cur_off;
+    *out = ctx->chunks[ctx->cur_chunk].p + ctx->cur_off;
     ctx->cur_off += bytes;
     ctx->used_total += bytes;
     return TC_OK;
 }
 
-WsMark tc_ws_mark(tc_ctx *ctx) { return WsMark{ctx->chunks.size(), ctx->cur_off, ctx->used_total}; }
+WsMark tc_ws_mark(tc_ctx *ctx) { return WsMark{ctx->cur_chunk, ctx->cur_off, ctx->used_total}; }
 void tc_ws_release(tc_ctx *ctx, WsMark m) {
-    // Only rewind inside the chunk that was current at mark time; later chunks stay
-    // allocated (they are coalesced by the next ws_reset) but are not reused before then.
-    if (ctx->chunks.size() == m.nchunks) {
-        ctx->cur_off = m.off;
-        ctx->used_total = m.used;
-    }
+    ctx->cur_chunk = m.nchunks;
+    ctx->cur_off = m.off;
+    ctx->used_total = m.used;
 }
 
 static __global__ void d2h_small_kernel(unsigned char *dst, const unsigned char *src, size_t bytes) {
