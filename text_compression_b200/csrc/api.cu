@@ -546,10 +546,8 @@ int blocks_packed_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nb
     const uint64_t worst = nmax + 3;
     uint8_t *d_text[2];
     RlePack pk[2];
-    uint32_t *d_count; // the 6-byte records never leave the device: one scratch copy serves both slots
-    int16_t *d_rsym;
-    TC_TRY(ws_alloc(ctx, worst, &d_count));
-    TC_TRY(ws_alloc(ctx, worst, &d_rsym));
+    uint32_t *d_count = nullptr; // the 6-byte records are never written: the RLE kernel emits the packed form
+    int16_t *d_rsym = nullptr;
     for (int s = 0; s < 2; s++) {
         TC_TRY(ws_alloc(ctx, nmax ? nmax : 1, &d_text[s]));
         TC_TRY(ws_alloc(ctx, al16(worst), &pk[s].cnt8));

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(RT)
     rle_reduce_kernel(In in, uint64_t N, uint32_t *__restrict__ tile_pairs, uint32_t *__restrict__ tile_head,
                       uint32_t *__restrict__ tile_just) {
     constexpr int ITEMS = In::ITEMS;
-    __shared__ uint32_t sh[RT / 32 + 1];
+    __shared__ uint32_t sh[3 * (RT / 32)];
     uint64_t base = ((uint64_t)blockIdx.x * RT + threadIdx.x) * ITEMS;
     int c[ITEMS];
     uint32_t pairs = 0, lh = 0, lj = 0;
@@ -112,11 +112,23 @@ __global__ void __launch_bounds__(RT)
             }
         }
     }
-    uint32_t tp, th, tj = 0;
-    block_excl_sum<uint32_t, RT>(pairs, sh, &tp);
-    block_excl_max<uint32_t, RT>(lh, 0u, sh, &th);
-    if (In::HAS_NOTHING) block_excl_max<uint32_t, RT>(lj, 0u, sh, &tj);
+    // tile totals only: warp reductions (redux.sync) and one round through shared memory
+    const uint32_t wp = __reduce_add_sync(TC_FULL, pairs), wh = __reduce_max_sync(TC_FULL, lh);
+    const uint32_t wj = In::HAS_NOTHING ? __reduce_max_sync(TC_FULL, lj) : 0u;
+    if (lane_id() == 0) {
+        sh[threadIdx.x >> 5] = wp;
+        sh[RT / 32 + (threadIdx.x >> 5)] = wh;
+        sh[2 * (RT / 32) + (threadIdx.x >> 5)] = wj;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        uint32_t tp = 0, th = 0, tj = 0;
+#pragma unroll
+        for (int w = 0; w < RT / 32; w++) {
+            tp += sh[w];
+            th = max(th, sh[RT / 32 + w]);
+            tj = max(tj, sh[2 * (RT / 32) + w]);
+        }
         tile_pairs[blockIdx.x] = tp;
         tile_head[blockIdx.x] = th;
         tile_just[blockIdx.x] = tj;
@@ -171,11 +183,20 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
-template <class In>
+struct PackArgs { // device pointers of RlePack, passed by value to the emit kernel
+    uint8_t *cnt8, *sym8;
+    uint32_t *hi;
+    uint64_t *big_idx;
+    uint32_t *big_cnt;
+    uint64_t big_cap;
+    unsigned long long *n_big;
+};
+
+template <class In, bool PACKED>
 __global__ void __launch_bounds__(RT)
     rle_emit_kernel(In in, uint64_t N, const uint64_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_headx,
                     const uint32_t *__restrict__ tile_justx, uint32_t *__restrict__ count, int16_t *__restrict__ rsym,
-                    uint64_t cap, uint64_t *__restrict__ d_R) {
+                    uint64_t cap, uint64_t *__restrict__ d_R, PackArgs pk) {
     constexpr int ITEMS = In::ITEMS;
     // + one Nothing's second pair + final flush + alignment pad, rounded up to the swizzle period
     constexpr int CAP = (In::MAX_PER_ITEM * RT * ITEMS + 3 + 8 + 63) / 64 * 64;
@@ -193,6 +214,34 @@ __global__ void __launch_bounds__(RT)
     // full 5-bit swizzle with a scalar copy-out measured the same (46-50 us).
     auto pc = [&](uint32_t slot) { uint32_t j = padc + slot; return j ^ (((j >> 5) & 3u) << 2); };
     auto ps = [&](uint32_t slot) { uint32_t j = pads + slot; return j ^ (((j >> 6) & 3u) << 3); };
+    // PACKED: the same storage holds the packed form instead -- one byte per count, one per symbol
+    // (consecutive bytes per thread: lanes 16 bytes apart, 4-way conflicts without any swizzle) and
+    // a bitmap of the symbols' bit 8 -- at staged index padp + slot with padp = goff mod 32, so
+    // 16-byte groups of the byte streams and 32-bit words of the bitmap line up with global memory
+    uint8_t *s_c8 = reinterpret_cast<uint8_t *>(s_cnt_raw);
+    uint8_t *s_s8 = reinterpret_cast<uint8_t *>(s_sym_raw);
+    __shared__ uint32_t s_hi[PACKED ? (CAP + 32) / 32 + 1 : 1];
+    const uint32_t padp = (uint32_t)(goff & 31);
+    if (PACKED)
+        for (uint32_t j = threadIdx.x; j < (CAP + 32) / 32 + 1; j += RT) s_hi[j] = 0; // block scans below sync
+    auto put = [&](uint32_t slot, uint32_t cnt, int sym) {
+        if (PACKED) {
+            const uint32_t j = padp + slot;
+            s_c8[j] = (uint8_t)min(cnt, 255u);
+            s_s8[j] = (uint8_t)sym;
+            if (sym & 0x100) atomicOr(&s_hi[j >> 5], 1u << (j & 31)); // MTF index 256, Nothing (-1)
+            if (cnt >= 255u) {
+                const unsigned long long e = atomicAdd(pk.n_big, 1ull);
+                if (e < pk.big_cap) {
+                    pk.big_idx[e] = goff + slot;
+                    pk.big_cnt[e] = cnt;
+                }
+            }
+        } else {
+            s_cnt_raw[pc(slot)] = cnt;
+            s_sym_raw[ps(slot)] = (int16_t)sym;
+        }
+    };
     uint64_t base = ((uint64_t)blockIdx.x * RT + threadIdx.x) * ITEMS;
     int c[ITEMS];
     int p0 = NOPREV;
@@ -242,18 +291,14 @@ __global__ void __launch_bounds__(RT)
                     if (p != NOPREV) {
                         if (ck < 0) {
                             if (p >= 0) {
-                                s_cnt_raw[pc(o)] = i - (H - 1);
-                                s_sym_raw[ps(o)] = (int16_t)p;
+                                put(o, i - (H - 1), p);
                             } else {
-                                s_cnt_raw[pc(o)] = J == 0 ? 1u : J - H + 1;
-                                s_sym_raw[ps(o)] = -1;
+                                put(o, J == 0 ? 1u : J - H + 1, -1);
                             }
-                            s_cnt_raw[pc(o + 1)] = 1;
-                            s_sym_raw[ps(o + 1)] = -1;
+                            put(o + 1, 1u, -1);
                             o += 2;
                         } else if (p >= 0 && p != ck) {
-                            s_cnt_raw[pc(o)] = i - (H - 1);
-                            s_sym_raw[ps(o)] = (int16_t)p;
+                            put(o, i - (H - 1), p);
                             o += 1;
                         }
                     }
@@ -263,19 +308,16 @@ __global__ void __launch_bounds__(RT)
                     }
                 } else if (p != ck) {
                     if (p != NOPREV) {
-                        s_cnt_raw[pc(o)] = i - (H - 1);
-                        s_sym_raw[ps(o)] = (int16_t)p;
+                        put(o, i - (H - 1), p);
                         o += 1;
                     }
                     H = i + 1;
                 }
                 if (owns_last && k == lim - 1) { // end-of-input flush (src/Data/RLE/Internal.hs:125-130)
                     if (ck >= 0) {
-                        s_cnt_raw[pc(o)] = (uint32_t)N - (H - 1);
-                        s_sym_raw[ps(o)] = (int16_t)ck;
+                        put(o, (uint32_t)N - (H - 1), ck);
                     } else {
-                        s_cnt_raw[pc(o)] = J == 0 ? 1u : J - H + 1;
-                        s_sym_raw[ps(o)] = -1;
+                        put(o, J == 0 ? 1u : J - H + 1, -1);
                     }
                     o += 1;
                 }
@@ -284,6 +326,35 @@ __global__ void __launch_bounds__(RT)
         }
     }
     __syncthreads();
+    if (PACKED) {
+        if (goff + tile_total <= cap) {
+            const uint64_t gp = goff - padp; // multiple of 32
+            const uint32_t nv = (padp + tile_total + 15) / 16;
+            for (uint32_t v = threadIdx.x; v < nv; v += RT) {
+                const uint32_t j0 = 16 * v;
+                if (j0 >= padp && j0 + 16 <= padp + tile_total) {
+                    *reinterpret_cast<uint4 *>(pk.cnt8 + gp + j0) = *reinterpret_cast<const uint4 *>(s_c8 + j0);
+                    *reinterpret_cast<uint4 *>(pk.sym8 + gp + j0) = *reinterpret_cast<const uint4 *>(s_s8 + j0);
+                } else {
+                    for (uint32_t j = j0; j < j0 + 16; j++)
+                        if (j >= padp && j < padp + tile_total) {
+                            pk.cnt8[gp + j] = s_c8[j];
+                            pk.sym8[gp + j] = s_s8[j];
+                        }
+                }
+            }
+            // hi plane in whole words; a word shared with a neighbouring tile is OR-ed into the
+            // plane, which is zeroed before the launch (bits outside the tile are 0 in s_hi)
+            const uint32_t nh = (padp + tile_total + 31) / 32;
+            for (uint32_t v = threadIdx.x; v < nh; v += RT) {
+                const uint32_t word = s_hi[v];
+                if (32 * v >= padp && 32 * v + 32 <= padp + tile_total) pk.hi[(gp >> 5) + v] = word;
+                else if (word) atomicOr(&pk.hi[(gp >> 5) + v], word);
+            }
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;
+        return;
+    }
     const bool vec_ok = goff + tile_total <= cap && (reinterpret_cast<uintptr_t>(count) & 15) == 0 &&
                         (reinterpret_cast<uintptr_t>(rsym) & 15) == 0;
     if (vec_ok) {
@@ -321,66 +392,15 @@ __global__ void __launch_bounds__(RT)
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;
 }
 
-
 // ---- packed run payload (block container) ------------------------------------
 // Runs leave the device as 2 bytes + 1 bit each instead of the 6-byte record:
 //   cnt8[k] = min(count, 255); sym8[k] = low byte of the symbol; hi bit k = bit 8 of the
 //   symbol's 9-bit code (set for MTF index 256 and for Nothing, whose code is 0x1ff);
-//   counts >= 255 are listed as (run index, count) exceptions, appended in arbitrary order here
-//   and sorted by run index before they leave the device.
-// One lane packs 8 consecutive runs: 48 B in (coalesced 128-bit loads), 17 B out.
-constexpr int PK_T = 256;
-__global__ void __launch_bounds__(PK_T)
-    rle_pack_kernel(const uint32_t *__restrict__ count, const int16_t *__restrict__ rsym,
-                    const uint64_t *__restrict__ d_R, uint64_t cap, uint2 *__restrict__ cnt8, uint2 *__restrict__ sym8,
-                    uint32_t *__restrict__ hi, uint64_t *__restrict__ big_idx, uint32_t *__restrict__ big_cnt,
-                    uint64_t big_cap, unsigned long long *__restrict__ n_big) {
-    const uint64_t R = min(*d_R, cap);
-    const uint64_t g = (uint64_t)blockIdx.x * PK_T + threadIdx.x; // group of 8 runs
-    const uint64_t k0 = g * 8;
-    if ((uint64_t)blockIdx.x * PK_T * 8 >= R) return; // whole CTA past the end
-    uint32_t c[8];
-    uint32_t s[8];
-    if (k0 + 8 <= R) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(count + k0);
-        const uint4 b = *reinterpret_cast<const uint4 *>(count + k0 + 4);
-        const uint4 v = *reinterpret_cast<const uint4 *>(rsym + k0);
-        c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 8; k++) s[k] = (w[k >> 1] >> ((k & 1) * 16)) & 0x1ffu;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const bool in = k0 + k < R;
-            c[k] = in ? count[k0 + k] : 0u;
-            s[k] = in ? ((uint32_t)(uint16_t)rsym[k0 + k] & 0x1ffu) : 0u;
-        }
-    }
-    uint32_t cw[2] = {0, 0}, sw[2] = {0, 0}, hb = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (c[k] >= 255u) {
-            const unsigned long long slot = atomicAdd(n_big, 1ull);
-            if (slot < big_cap) {
-                big_idx[slot] = k0 + k;
-                big_cnt[slot] = c[k];
-            }
-        }
-        cw[k >> 2] |= min(c[k], 255u) << ((k & 3) * 8);
-        sw[k >> 2] |= (s[k] & 0xffu) << ((k & 3) * 8);
-        hb |= (s[k] >> 8) << k;
-    }
-    // four lanes share one 32-bit word of the hi plane
-    hb <<= 8 * (threadIdx.x & 3);
-    hb |= __shfl_xor_sync(TC_FULL, hb, 1);
-    hb |= __shfl_xor_sync(TC_FULL, hb, 2);
-    if (k0 < R) {
-        cnt8[g] = make_uint2(cw[0], cw[1]);
-        sym8[g] = make_uint2(sw[0], sw[1]);
-    }
-    if ((threadIdx.x & 3) == 0 && k0 < R) hi[g >> 2] = hb;
-}
+//   counts >= 255 are listed as (run index, count) exceptions, appended in arbitrary order by
+//   the emit kernel and sorted by run index before they leave the device.
+// rle_emit_kernel<In, true> stages this form in shared memory and writes it straight out (the
+// 6-byte records are never written): byte streams in aligned groups of 16 runs, the hi plane in
+// whole 32-run words, with atomicOr on the (zeroed) words a tile shares with its neighbours.
 
 // inverse of the packing for the device-side decoder: one thread per run; exceptions patched after
 __global__ void rle_unpack_kernel(const uint8_t *__restrict__ cnt8, const uint8_t *__restrict__ sym8,
@@ -436,17 +456,17 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
     // NB: the reduce kernel's tile pair counts exclude the final flush; the emit kernel adds it
     // for the owner of position N-1, which is always in the last tile, so offsets stay exact.
     TC_LAUNCH(ctx, rle_tile_scan_kernel, 1, 1024, 0, tp, th, tj, toff, tiles);
-    TC_LAUNCH(ctx, (rle_emit_kernel<In>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap, d_R);
     if (pk) {
-        // d_R and the exception counter sit next to each other so that one small copy brings both
-        // back; the pack grid covers the capacity and CTAs past R leave at once, so no host
-        // sync separates the emit kernel from the packing.
+        // d_R and the exception counter sit next to each other so that one small copy brings both back
         pk->n_big = 0;
         TC_CUDA(cudaMemsetAsync(d_R + 1, 0, sizeof(uint64_t), ctx->stream));
-        const uint64_t groups = ceil_div_u64(cap, 8);
-        TC_LAUNCH(ctx, rle_pack_kernel, (unsigned)ceil_div_u64(groups, PK_T), PK_T, 0, d_count, d_rsym, d_R, cap,
-                  (uint2 *)pk->cnt8, (uint2 *)pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap,
-                  (unsigned long long *)(d_R + 1));
+        TC_CUDA(cudaMemsetAsync(pk->hi, 0, ceil_div_u64(cap, 32) * sizeof(uint32_t), ctx->stream));
+        PackArgs pa{pk->cnt8, pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap, (unsigned long long *)(d_R + 1)};
+        TC_LAUNCH(ctx, (rle_emit_kernel<In, true>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap, d_R,
+                  pa);
+    } else {
+        TC_LAUNCH(ctx, (rle_emit_kernel<In, false>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap,
+                  d_R, PackArgs{});
     }
     TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, (pk ? 2 : 1) * sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));

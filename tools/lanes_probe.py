@@ -27,3 +27,11 @@ def batch(nb):
 for nb in (3, 10, 10, 10, 20, 40):
     t = batch(nb)
     print(f"lanes={os.environ.get('TC_B200_LANES','2')} nb={nb}: {1e3*t:.2f} ms = {1e3*t/nb:.3f} ms/block = {nb*n/1e6/t:.0f} MB/s", flush=True)
+ctx.profile(True)      # profiling keeps the batch on one lane: per-kernel times of the packed path
+batch(3)
+rep = ctx.profile_report()
+ctx.profile(False)
+for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+    if k.startswith("rle") or k.startswith("(rle"):
+        print(f"  {k[:46]:46s} x{v[0]/3:5.1f} {v[1]/3*1e3:9.1f} us")
+print(f"  all kernels: {sum(v[1] for v in rep.values())/3:.3f} ms/block")
