@@ -14,6 +14,14 @@ rep = np.tile(gen_acgtn(3, 3000), 8)          # repeats: ties, deep compare, dou
 b = block.compress_bwt_mtf_rle(rep, ctx)
 assert block.decompress(b, ctx) == rep.tobytes()
 bl = block.compress_blocks([gen_bytes(1, 50000), gen_acgtn(2, 80000), np.empty(0, np.uint8)], True, ctx)
+texts = [gen_bytes(1, 50000), gen_acgtn(2, 80000), np.empty(0, np.uint8), np.frombuffer(b"a" * 9000 + b"bc" * 500, np.uint8),
+         np.tile(np.arange(256, dtype=np.uint8), 30), gen_ascii(4, 4099)]
+for with_mtf in (True, False):
+    for blob, t in zip(block.compress_blocks_packed(texts, with_mtf, ctx), texts):
+        u = block.unpack_block(blob)
+        assert int(u.counts.sum()) == (t.size + 1 if t.size else 0) or not with_mtf
+        if with_mtf:
+            assert block.decompress_packed(blob, ctx) == t.tobytes()
 fm = fmindex.FMIndex(gen_acgtn(0xC3, 100000), "B", 32, ctx)
 pats = [gen_acgtn(0xC3, 100000)[o:o + 20].tobytes() for o in range(0, 50000, 501)]
 c = fm.count_many(pats)
