@@ -87,6 +87,17 @@ foreign import ccall safe "tc_bwt_mtf_rle_encode"
 foreign import ccall safe "tc_blocks_encode"
   c_blocks_encode :: Ptr TcCtx -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> CInt -> Ptr (Ptr Word32)
                   -> Ptr (Ptr Int16) -> Ptr Word64 -> Ptr () -> IO CInt
+-- same, with one packed block container per block as output (tc_packed_header + cnt8 / sym8 / hi
+-- sections): a third of the bytes over PCIe, and a single ByteString per block on the Haskell side
+foreign import ccall safe "tc_packed_bound" c_packed_bound :: Word64 -> IO Word64
+foreign import ccall safe "tc_blocks_encode_packed"
+  c_blocks_encode_packed :: Ptr TcCtx -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> CInt -> Ptr (Ptr Word8)
+                         -> Ptr Word64 -> Ptr Word64 -> Ptr () -> IO CInt
+-- host only: container -> the (count, symbol) records of tc_blocks_encode
+foreign import ccall unsafe "tc_packed_unpack"
+  c_packed_unpack :: Ptr Word8 -> Word64 -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr () -> IO CInt
+foreign import ccall safe "tc_packed_decode"
+  c_packed_decode :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Ptr Word8 -> Word64 -> Ptr Word64 -> IO CInt
 foreign import ccall safe "tc_fm_build"
   c_fm_build :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Word32 -> Ptr (Ptr TcFm) -> IO CInt
 foreign import ccall safe "&tc_fm_free" p_fm_free :: FunPtr (Ptr TcFm -> IO ())
