@@ -8,8 +8,10 @@ A step = one pass of the hot path over one 16 MiB block of synthetic random byte
 (BASELINE.json configs[1]; the multi-block config 5 partitions such blocks over the GPUs, so
 N GPUs process N blocks per step with no data-path collective: weak scaling).
 
-Timed region of `value`: inputs already resident in HBM, CUDA events on the launching stream,
-barrier + synchronize on both sides, max over ranks.  `e2e` is the same metric through the
+Timed region of `value`: inputs already resident in HBM, K steps = K blocks through one
+tc_blocks_encode_dev call (texts and runs stay in HBM, two blocks in flight per GPU; the time of
+one block at a time is reported in `config`), CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  `e2e` is the same metric through the
 host-buffer C-ABI call (tc_blocks_encode_packed: text in pinned host memory in, packed block
 containers in pinned host memory out) with every block's H2D and D2H inside the timed region;
 the record-output call (tc_blocks_encode) and the single-block call are timed beside it.  Inputs rotate over 12 distinct blocks (192 MiB > the 126 MB L2) and every
@@ -199,15 +201,27 @@ def run_b200(args):
     for b in range(NBLOCKS):
         d_text[b].copy_(torch.from_numpy(host_blocks[b]))
     cap = n + 3
-    d_count = torch.empty(cap, dtype=torch.int32, device="cuda")
-    d_rsym = torch.empty(cap, dtype=torch.int16, device="cuda")
+    d_count = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(2)]
+    d_rsym = [torch.empty(cap, dtype=torch.int16, device="cuda") for _ in range(2)]
     torch.cuda.synchronize()
     info = BlockInfo()
 
-    def step_dev(i):
+    def step_dev(i):   # one block, one call (the profile pass and the single-block figure)
         b = i % NBLOCKS
-        ctx.call("tc_bwt_mtf_rle_encode_dev", C.c_void_p(d_text[b].data_ptr()), n, C.c_void_p(d_count.data_ptr()),
-                 C.c_void_p(d_rsym.data_ptr()), cap, C.byref(info))
+        ctx.call("tc_bwt_mtf_rle_encode_dev", C.c_void_p(d_text[b].data_ptr()), n, C.c_void_p(d_count[0].data_ptr()),
+                 C.c_void_p(d_rsym[0].data_ptr()), cap, C.byref(info))
+
+    def steps_dev(first, k):
+        """k steps = k blocks through tc_blocks_encode_dev: texts and runs stay in HBM, two blocks in flight
+        (block i writes the run buffers of lane i % 2)."""
+        tp = (C.c_void_p * k)(*[d_text[(first + i) % NBLOCKS].data_ptr() for i in range(k)])
+        cp = (C.c_void_p * k)(*[d_count[i % 2].data_ptr() for i in range(k)])
+        sp = (C.c_void_p * k)(*[d_rsym[i % 2].data_ptr() for i in range(k)])
+        ns = (C.c_uint64 * k)(*([n] * k))
+        caps = (C.c_uint64 * k)(*([cap] * k))
+        infos = (BlockInfo * k)()
+        ctx.call("tc_blocks_encode_dev", k, tp, ns, 1, cp, sp, caps, infos)
+        return infos
 
     def barrier():
         if world > 1:
@@ -220,8 +234,8 @@ def run_b200(args):
         t_w = time.perf_counter()
         i = 0
         while i < args.warmup or time.perf_counter() - t_w < 0.25:
-            step_dev(i)
-            i += 1
+            steps_dev(i, max(args.warmup, 2))
+            i += max(args.warmup, 2)
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:   # the line reports rank 0's clocks; NVML polling from every rank contends on the driver
@@ -229,8 +243,7 @@ def run_b200(args):
         launches0 = ctx.launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        for i in range(args.steps):
-            step_dev(args.warmup + i)
+        infos = steps_dev(args.warmup, args.steps)   # returns with both lanes drained
         ev1.record(stream)
         barrier()
         launches = ctx.launches - launches0
@@ -240,12 +253,23 @@ def run_b200(args):
         ms = ev0.elapsed_time(ev1)
         if os.environ.get("TC_BENCH_DEBUG"):
             print(f"[rank {rank}] {ms / args.steps:.4f} ms/step", file=sys.stderr)
+        info = infos[args.steps - 1]
         R_last = int(info.R)
+        sigma = int(info.sigma)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         value = world * args.steps * n / 1e6 / (ms / 1e3)
+        # one block at a time (no second block to fill the serial phases of the kernel chain)
+        info = BlockInfo()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record(stream)
+        for i in range(args.steps):
+            step_dev(args.warmup + i)
+        ev3.record(stream)
+        torch.cuda.synchronize()
+        single_ms = ev2.elapsed_time(ev3) / args.steps
 
         # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region.  The call is
         # tc_blocks_encode_packed, the multi-block entry point with container output: one call
@@ -355,8 +379,10 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "block_bytes": n, "blocks_per_step": world, "sigma": int(info.sigma),
+            "config": {"workload": WORKLOAD, "block_bytes": n, "blocks_per_step": world, "sigma": sigma,
                        "runs_per_block": R_last,
+                       "api": "tc_blocks_encode_dev: one call over `steps` HBM-resident blocks, two blocks in flight per GPU",
+                       "one_block_at_a_time_ms_per_step": single_ms,
                        "warmup_note": "W untimed steps, extended to >= 0.25 s so all GPUs leave idle clocks",
                        "l2": f"inputs rotate over {NBLOCKS} distinct blocks ({NBLOCKS * n >> 20} MiB > L2); "
                              "each step streams > 1 GB of sort traffic"},

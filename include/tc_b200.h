@@ -190,6 +190,13 @@ int tc_rle_encode_u16_dev(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32
 int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *d_count, int16_t *d_rsym,
                               uint64_t cap, tc_block_info *info);
 
+/* tc_blocks_encode on device pointers: d_text[b], d_count[b], d_rsym[b] live in HBM, nothing is copied.
+ * Blocks are compressed two at a time (the caller's context and a child context on a helper thread),
+ * which fills the short serial phases of one block's kernel chain with the other block's kernels;
+ * blocks processed concurrently must not share output buffers (block b and b+1 run together). */
+int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *d_text, const uint64_t *n, int with_mtf,
+                         uint32_t *const *d_count, int16_t *const *d_rsym, const uint64_t *cap, tc_block_info *info);
+
 /* ---- Data.FMIndex ------------------------------------------------------------ */
 /* *ToBWTToFMIndex* (src/Data/FMIndex.hs:108-183): C[c] (seqToCc, Internal.hs:275-316),
  * Occ (seqToOccCK, :195-259; stored as rank-blocks instead of the dense table) and the

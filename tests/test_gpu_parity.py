@@ -451,6 +451,42 @@ def test_packed_container(ctx, orc):
                 assert block.decompress_packed(blob, ctx) == t.tobytes()
 
 
+def test_device_resident_batch(ctx):
+    """tc_blocks_encode_dev (texts and runs stay in HBM, two blocks in flight) and the single-block
+    tc_bwt_mtf_rle_encode_dev give, block by block, the records of the host-buffer call."""
+    import ctypes as C
+    import torch
+    from text_compression_b200 import block
+    from text_compression_b200._lib import BlockInfo
+    texts = [gen_bytes(11, 150001), gen_acgtn(12, 90000), gen_ascii(13, 4097), np.empty(0, np.uint8), gen_bytes(14, 70000),
+             gen_acgt(15, 33), gen_acgtn(16, 250000)]
+    nb = len(texts)
+    d_text = [torch.from_numpy(t.copy()).cuda() if t.size else torch.empty(1, dtype=torch.uint8, device="cuda") for t in texts]
+    d_cnt = [torch.empty(t.size + 3, dtype=torch.int32, device="cuda") for t in texts]
+    d_sym = [torch.empty(t.size + 3, dtype=torch.int16, device="cuda") for t in texts]
+    torch.cuda.synchronize()
+    for with_mtf in (1, 0):
+        tp = (C.c_void_p * nb)(*[x.data_ptr() for x in d_text])
+        cp = (C.c_void_p * nb)(*[x.data_ptr() for x in d_cnt])
+        sp = (C.c_void_p * nb)(*[x.data_ptr() for x in d_sym])
+        ns = (C.c_uint64 * nb)(*[t.size for t in texts])
+        caps = (C.c_uint64 * nb)(*[t.size + 3 for t in texts])
+        infos = (BlockInfo * nb)()
+        ctx.call("tc_blocks_encode_dev", nb, tp, ns, with_mtf, cp, sp, caps, infos)
+        for b, t in enumerate(texts):
+            one = (block.compress_bwt_mtf_rle if with_mtf else block.compress_bwt_rle)(t, ctx)
+            R = int(infos[b].R)
+            assert (R, int(infos[b].primary), int(infos[b].sigma)) == (one.R, one.primary, one.sigma)
+            assert np.array_equal(d_cnt[b][:R].cpu().numpy().view(np.uint32), one.counts)
+            assert np.array_equal(d_sym[b][:R].cpu().numpy(), one.syms)
+            assert list(infos[b].final_list[: one.sigma]) == one.final_list.tolist()
+    info = BlockInfo()
+    ctx.call("tc_bwt_mtf_rle_encode_dev", C.c_void_p(d_text[0].data_ptr()), texts[0].size, C.c_void_p(d_cnt[1].data_ptr()),
+             C.c_void_p(d_sym[1].data_ptr()), texts[1].size + 3, C.byref(info), allow=(-2,))
+    one = block.compress_bwt_mtf_rle(texts[0], ctx)
+    assert int(info.R) == one.R       # capacity of block 1's buffers is too small: TC_E_CAP, R still reported
+
+
 def test_q1_trailing_nothing_stream(ctx, orc):
     """Texts that are their own greatest suffix: the reference's RLE re-emits a stale pair (Q1)
     and its own round trip breaks; the GPU stream must equal the oracle's, not round-trip."""

@@ -89,6 +89,7 @@ _SIGS = {
     "tc_rle_encode_u8_dev": (_int, [_vp, _vp, _u64, _u64, _vp, _vp, _u64, _pu64]),
     "tc_rle_encode_u16_dev": (_int, [_vp, _vp, _u64, _vp, _vp, _u64, _pu64]),
     "tc_bwt_mtf_rle_encode_dev": (_int, [_vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(BlockInfo)]),
+    "tc_blocks_encode_dev": (_int, [_vp, _u64, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(BlockInfo)]),
     "tc_fm_build": (_int, [_vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "tc_fm_build_dev": (_int, [_vp, _vp, _u64, _u32, C.POINTER(_vp)]),
     "tc_fm_free": (None, [_vp]),

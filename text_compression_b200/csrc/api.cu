@@ -645,6 +645,49 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
     return rc1;
 }
 
+// Device-resident batch (bench `value`, HBM-resident callers): texts and run records stay in HBM, no
+// copies; the same two lanes as tc_blocks_encode_packed, so the serial phases of one block's
+// kernel chain are filled by the other block's kernels.
+namespace {
+int blocks_dev_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nblocks, const uint8_t *const *d_text,
+                    const uint64_t *n, int with_mtf, uint32_t *const *d_count, int16_t *const *d_rsym,
+                    const uint64_t *cap, tc_block_info *info) {
+    int rc_all = TC_OK;
+    for (uint64_t b = first; b < nblocks; b += stride) {
+        TC_TRY(tc_ws_reset(ctx));
+        int rc = compress_dev(ctx, d_text[b], n[b], with_mtf != 0, d_count[b], d_rsym[b], cap[b], &info[b]);
+        if (rc == TC_E_CAP) rc_all = rc;
+        else if (rc != TC_OK) return rc;
+    }
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return rc_all;
+}
+} // namespace
+
+extern "C" int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *d_text, const uint64_t *n,
+                                    int with_mtf, uint32_t *const *d_count, int16_t *const *d_rsym, const uint64_t *cap,
+                                    tc_block_info *info) {
+    if (!ctx) return TC_E_ARG;
+    if (nblocks == 0) return TC_OK;
+    if (!d_text || !n || !d_count || !d_rsym || !cap || !info) return TC_E_ARG;
+    for (uint64_t b = 0; b < nblocks; b++)
+        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+    const bool two = ctx->lanes >= 2 && nblocks >= 2 && !ctx->prof_on;
+    if (two && !ctx->child) TC_TRY(tc_ctx_create(ctx->device, &ctx->child));
+    if (!two) return blocks_dev_lane(ctx, 0, 1, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
+    // work queued earlier on the caller's stream (e.g. the producer of the texts) must be visible to the child lane
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    int rc1 = TC_OK;
+    std::thread helper([&] { rc1 = blocks_dev_lane(ctx->child, 1, 2, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info); });
+    int rc0 = blocks_dev_lane(ctx, 0, 2, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
+    helper.join();
+    if (rc1 != TC_OK && rc1 != TC_E_CAP) {
+        memcpy(ctx->err, ctx->child->err, sizeof ctx->err);
+        return rc1;
+    }
+    return rc0 != TC_OK ? rc0 : rc1;
+}
+
 extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap,
                                 uint64_t *n_out) {
     TC_ENTER(ctx);
