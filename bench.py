@@ -9,7 +9,7 @@ A step = one pass of the hot path over one 16 MiB block of synthetic random byte
 N GPUs process N blocks per step with no data-path collective: weak scaling).
 
 Timed region of `value`: inputs already resident in HBM, K steps = K blocks through one
-tc_blocks_encode_dev call (texts and runs stay in HBM, two blocks in flight per GPU; the time of
+tc_blocks_encode_dev call (texts and runs stay in HBM, three blocks in flight per GPU; the time of
 one block at a time is reported in `config`), CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks.  `e2e` is the same metric through the
 host-buffer C-ABI call (tc_blocks_encode_packed: text in pinned host memory in, packed block
@@ -201,8 +201,9 @@ def run_b200(args):
     for b in range(NBLOCKS):
         d_text[b].copy_(torch.from_numpy(host_blocks[b]))
     cap = n + 3
-    d_count = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(2)]
-    d_rsym = [torch.empty(cap, dtype=torch.int16, device="cuda") for _ in range(2)]
+    NOUT = 4   # run buffers: blocks in flight never share one (at most 4 lanes)
+    d_count = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(NOUT)]
+    d_rsym = [torch.empty(cap, dtype=torch.int16, device="cuda") for _ in range(NOUT)]
     torch.cuda.synchronize()
     info = BlockInfo()
 
@@ -212,11 +213,11 @@ def run_b200(args):
                  C.c_void_p(d_rsym[0].data_ptr()), cap, C.byref(info))
 
     def steps_dev(first, k):
-        """k steps = k blocks through tc_blocks_encode_dev: texts and runs stay in HBM, two blocks in flight
-        (block i writes the run buffers of lane i % 2)."""
+        """k steps = k blocks through tc_blocks_encode_dev: texts and runs stay in HBM, three blocks in flight
+        (block i writes run buffer i % NOUT)."""
         tp = (C.c_void_p * k)(*[d_text[(first + i) % NBLOCKS].data_ptr() for i in range(k)])
-        cp = (C.c_void_p * k)(*[d_count[i % 2].data_ptr() for i in range(k)])
-        sp = (C.c_void_p * k)(*[d_rsym[i % 2].data_ptr() for i in range(k)])
+        cp = (C.c_void_p * k)(*[d_count[i % NOUT].data_ptr() for i in range(k)])
+        sp = (C.c_void_p * k)(*[d_rsym[i % NOUT].data_ptr() for i in range(k)])
         ns = (C.c_uint64 * k)(*([n] * k))
         caps = (C.c_uint64 * k)(*([cap] * k))
         infos = (BlockInfo * k)()
@@ -234,8 +235,8 @@ def run_b200(args):
         t_w = time.perf_counter()
         i = 0
         while i < args.warmup or time.perf_counter() - t_w < 0.25:
-            steps_dev(i, max(args.warmup, 2))
-            i += max(args.warmup, 2)
+            steps_dev(i, max(args.warmup, 4))   # >= the number of lanes: every lane's context and arena exist
+            i += max(args.warmup, 4)
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:   # the line reports rank 0's clocks; NVML polling from every rank contends on the driver
@@ -304,7 +305,7 @@ def run_b200(args):
             return infos, int(infos[nb - 1].R) * 6
 
         def timed_batch(packed):
-            batch(max(3, min(args.warmup, 4)), packed)
+            batch(max(4, args.warmup), packed)
             barrier()
             t0 = time.perf_counter()
             _, nbytes = batch(args.steps, packed)
@@ -381,7 +382,7 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "block_bytes": n, "blocks_per_step": world, "sigma": sigma,
                        "runs_per_block": R_last,
-                       "api": "tc_blocks_encode_dev: one call over `steps` HBM-resident blocks, two blocks in flight per GPU",
+                       "api": "tc_blocks_encode_dev: one call over `steps` HBM-resident blocks, three blocks in flight per GPU (lanes)",
                        "one_block_at_a_time_ms_per_step": single_ms,
                        "warmup_note": "W untimed steps, extended to >= 0.25 s so all GPUs leave idle clocks",
                        "l2": f"inputs rotate over {NBLOCKS} distinct blocks ({NBLOCKS * n >> 20} MiB > L2); "
@@ -389,7 +390,7 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_val, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
                     "api": "tc_blocks_encode_packed: one call over `steps` blocks, pinned host buffers in and out, "
-                           "copies of neighbouring blocks overlapped with compute, two blocks in flight (two lanes: contexts + "
+                           "copies of neighbouring blocks overlapped with compute, three blocks in flight (lanes: contexts + "
                            "host threads inside the call); output = packed block container "
                            "(header + runs at 2 B + 1 bit each, lossless: tc_packed_unpack returns the records)",
                     "record_output_MBps": e2e_records, "record_output_d2h_bytes_per_step": d2h_records,

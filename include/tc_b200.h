@@ -191,9 +191,10 @@ int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, ui
                               uint64_t cap, tc_block_info *info);
 
 /* tc_blocks_encode on device pointers: d_text[b], d_count[b], d_rsym[b] live in HBM, nothing is copied.
- * Blocks are compressed two at a time (the caller's context and a child context on a helper thread),
- * which fills the short serial phases of one block's kernel chain with the other block's kernels;
- * blocks processed concurrently must not share output buffers (block b and b+1 run together). */
+ * Blocks are compressed `lanes` at a time (3 by default, TC_B200_LANES = 1..4: the caller's context plus
+ * child contexts on helper threads), which fills the short serial phases of one block's kernel chain
+ * with the other blocks' kernels; blocks b .. b + lanes - 1 run together and must not share output
+ * buffers. */
 int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *d_text, const uint64_t *n, int with_mtf,
                          uint32_t *const *d_count, int16_t *const *d_rsym, const uint64_t *cap, tc_block_info *info);
 

@@ -610,9 +610,43 @@ int blocks_packed_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nb
 }
 } // namespace
 
-// Two lanes by default (TC_B200_LANES): even blocks on the caller's context and thread, odd blocks
-// on a child context driven by a helper thread.  Each block's kernel chain has short serial phases
-// (single-CTA scans, two host syncs); with two blocks in flight the other lane's kernels fill them.
+namespace {
+// Runs fn(lane context, first block, stride) on `lanes` lanes: lane 0 on the caller's context and
+// thread, the others on child contexts driven by helper threads.  TC_E_CAP from any lane is
+// reported after all lanes have finished; any other error wins.
+template <class F>
+int run_lanes(tc_ctx *ctx, uint64_t nblocks, F fn) {
+    int lanes = ctx->prof_on ? 1 : ctx->lanes;
+    if ((uint64_t)lanes > nblocks) lanes = (int)nblocks;
+    for (int l = 1; l < lanes; l++)
+        if (!ctx->child[l - 1]) TC_TRY(tc_ctx_create(ctx->device, &ctx->child[l - 1]));
+    if (lanes <= 1) return fn(ctx, (uint64_t)0, (uint64_t)1);
+    // work queued earlier on the caller's stream (e.g. the producer of device-resident texts) must be
+    // visible to the other lanes' streams
+    TC_CUDA(cudaStreamSynchronize(ctx->stream));
+    int rc[tc_ctx::MAX_LANES] = {TC_OK, TC_OK, TC_OK, TC_OK};
+    std::thread th[tc_ctx::MAX_LANES - 1];
+    for (int l = 1; l < lanes; l++)
+        th[l - 1] = std::thread([&, l] { rc[l] = fn(ctx->child[l - 1], (uint64_t)l, (uint64_t)lanes); });
+    rc[0] = fn(ctx, (uint64_t)0, (uint64_t)lanes);
+    for (int l = 1; l < lanes; l++) th[l - 1].join();
+    int out = TC_OK;
+    for (int l = 0; l < lanes; l++) {
+        if (rc[l] == TC_OK) continue;
+        if (rc[l] != TC_E_CAP) {
+            if (l) memcpy(ctx->err, ctx->child[l - 1]->err, sizeof ctx->err);
+            return rc[l];
+        }
+        out = TC_E_CAP;
+    }
+    return out;
+}
+} // namespace
+
+// Three lanes by default (TC_B200_LANES = 1..4): block b runs on lane b mod lanes; lane 0 is the caller's
+// context and thread, the others are child contexts driven by helper threads.  Each block's kernel
+// chain has short serial phases (single-CTA scans, two host syncs); with several blocks in flight
+// the other lanes' kernels fill them.
 extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n,
                                        int with_mtf, uint8_t *const *out, const uint64_t *cap, uint64_t *out_bytes,
                                        tc_block_info *info) {
@@ -625,28 +659,13 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
         nmax = n[b] > nmax ? n[b] : nmax;
         out_bytes[b] = 0;
     }
-    const bool two = ctx->lanes >= 2 && nblocks >= 2 && !ctx->prof_on;
-    if (two && !ctx->child) {
-        int rc = tc_ctx_create(ctx->device, &ctx->child);
-        if (rc != TC_OK) return rc;
-    }
-    if (!two) return blocks_packed_lane(ctx, 0, 1, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
-    int rc1 = TC_OK;
-    std::thread helper([&] {
-        rc1 = blocks_packed_lane(ctx->child, 1, 2, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
+    return run_lanes(ctx, nblocks, [&](tc_ctx *c, uint64_t first, uint64_t stride) {
+        return blocks_packed_lane(c, first, stride, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
     });
-    int rc0 = blocks_packed_lane(ctx, 0, 2, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
-    helper.join();
-    if (rc1 != TC_OK && rc1 != TC_E_CAP) {
-        memcpy(ctx->err, ctx->child->err, sizeof ctx->err);
-        return rc1;
-    }
-    if (rc0 != TC_OK) return rc0;
-    return rc1;
 }
 
 // Device-resident batch (bench `value`, HBM-resident callers): texts and run records stay in HBM, no
-// copies; the same two lanes as tc_blocks_encode_packed, so the serial phases of one block's
+// copies; the same lanes as tc_blocks_encode_packed, so the serial phases of one block's
 // kernel chain are filled by the other block's kernels.
 namespace {
 int blocks_dev_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nblocks, const uint8_t *const *d_text,
@@ -672,20 +691,9 @@ extern "C" int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t
     if (!d_text || !n || !d_count || !d_rsym || !cap || !info) return TC_E_ARG;
     for (uint64_t b = 0; b < nblocks; b++)
         if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
-    const bool two = ctx->lanes >= 2 && nblocks >= 2 && !ctx->prof_on;
-    if (two && !ctx->child) TC_TRY(tc_ctx_create(ctx->device, &ctx->child));
-    if (!two) return blocks_dev_lane(ctx, 0, 1, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
-    // work queued earlier on the caller's stream (e.g. the producer of the texts) must be visible to the child lane
-    TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    int rc1 = TC_OK;
-    std::thread helper([&] { rc1 = blocks_dev_lane(ctx->child, 1, 2, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info); });
-    int rc0 = blocks_dev_lane(ctx, 0, 2, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
-    helper.join();
-    if (rc1 != TC_OK && rc1 != TC_E_CAP) {
-        memcpy(ctx->err, ctx->child->err, sizeof ctx->err);
-        return rc1;
-    }
-    return rc0 != TC_OK ? rc0 : rc1;
+    return run_lanes(ctx, nblocks, [&](tc_ctx *c, uint64_t first, uint64_t stride) {
+        return blocks_dev_lane(c, first, stride, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
+    });
 }
 
 extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap,

@@ -42,10 +42,11 @@ struct tc_ctx {
         int16_t *final_list = nullptr;
     } mtf_pending;
     uint32_t text_hist[256] = {0}; // byte histogram of the last text handed to the suffix sort
-    // second lane of the packed batch entry point (tc_blocks_encode_packed): a full context of its
-    // own on the same device, driven by a helper thread; created on first use
-    tc_ctx *child = nullptr;
-    int lanes = 2; // TC_B200_LANES=1: one block in flight
+    // extra lanes of the batch entry points (tc_blocks_encode_packed / _dev): full contexts of their
+    // own on the same device, each driven by a helper thread; created on first use
+    static constexpr int MAX_LANES = 4;
+    tc_ctx *child[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+    int lanes = 3; // blocks in flight per call (TC_B200_LANES=1..4; measured 2: 18.8, 3: 19.6, 4: 19.8 GB/s on C2)
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     char err[512] = {0};
     // optional per-kernel timing (tc_ctx_profile): one event pair per launch

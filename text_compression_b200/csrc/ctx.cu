@@ -24,7 +24,10 @@ extern "C" const char *tc_strerror(int rc) {
 
 extern "C" const char *tc_last_error(const tc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t tc_ctx_launches(const tc_ctx *ctx) {
-    return ctx ? ctx->launches + (ctx->child ? ctx->child->launches : 0) : 0;
+    if (!ctx) return 0;
+    uint64_t t = ctx->launches;
+    for (tc_ctx *c : ctx->child) t += c ? c->launches : 0;
+    return t;
 }
 
 static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc_ctx **out) {
@@ -45,7 +48,7 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     const char *nm = getenv("TC_B200_NO_MSD");
     ctx->no_msd = nm && nm[0] == '1';
     const char *ln = getenv("TC_B200_LANES");
-    if (ln && ln[0] >= '1' && ln[0] <= '2') ctx->lanes = ln[0] - '0';
+    if (ln && ln[0] >= '1' && ln[0] <= '0' + tc_ctx::MAX_LANES) ctx->lanes = ln[0] - '0';
     if (have_stream) {
         ctx->stream = stream;
         ctx->own_stream = false;
@@ -72,7 +75,7 @@ extern "C" int tc_ctx_create_on_stream(int device, void *cuda_stream, tc_ctx **o
 
 extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
     if (!ctx) return;
-    if (ctx->child) tc_ctx_destroy(ctx->child);
+    for (tc_ctx *c : ctx->child) tc_ctx_destroy(c);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &c : ctx->chunks) cudaFree(c.p);
