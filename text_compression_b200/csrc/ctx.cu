@@ -210,6 +210,7 @@ static __global__ void d2h_small_kernel(unsigned char *dst, const unsigned char 
 int tc_d2h_small(tc_ctx *ctx, void *h_pinned_dst, const void *d_src, size_t bytes) {
     if (bytes == 0) return TC_OK;
     d2h_small_kernel<<<1, 256, 0, ctx->stream>>>((unsigned char *)h_pinned_dst, (const unsigned char *)d_src, bytes);
+    ctx->launches++;
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return ctx->fail(e, "d2h_small_kernel", __LINE__);
     return TC_OK;
