@@ -62,7 +62,7 @@ def ncu_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
     ncu --set full capture of this workload (profiles/, produced by tools/make_profiles.sh)."""
     import csv
-    path = os.path.join(ROOT, "profiles", f"r1_ncu_full_summary_{ALPHABET}.csv")
+    path = os.path.join(ROOT, "profiles", f"r1e_ncu_full_summary_{ALPHABET}.csv")
     short = kernel.split("<")[0].strip()
     try:
         rows = list(csv.reader(open(path)))
@@ -305,7 +305,7 @@ def run_b200(args):
             return infos, int(infos[nb - 1].R) * 6
 
         def timed_batch(packed):
-            batch(max(4, args.warmup), packed)
+            batch(max(8, args.warmup), packed)   # lanes claim two blocks each: every lane (context, arena, streams) is warm
             barrier()
             t0 = time.perf_counter()
             _, nbytes = batch(args.steps, packed)

@@ -2,6 +2,7 @@
 // composed helpers.  Host entry points stage through the scratch arena (H2D, kernels, D2H on
 // the context's stream); `_dev` entry points work on device pointers.  Every entry point
 // resets the arena exactly once; the *_impl functions never do.
+#include <atomic>
 #include <thread>
 
 #include "common.cuh"
@@ -536,9 +537,11 @@ extern "C" int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *coun
 }
 
 namespace {
-// One lane of the packed batch: blocks first, first + stride, ... through one context (its stream,
-// its two copy streams, double buffers: slot = k & 1 for the lane's k-th block).
-int blocks_packed_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nblocks, uint64_t nmax,
+// One lane of the packed batch through one context (its stream, its two copy streams, double buffers:
+// slot = k & 1 for the lane's k-th block).  Lanes claim blocks from a shared counter, one block
+// ahead of the one they compress (its H2D is in flight meanwhile), so ragged block sizes and
+// block counts that are not a multiple of the lane count still keep every lane busy to the end.
+int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, uint64_t nblocks, uint64_t nmax,
                        const uint8_t *const *text, const uint64_t *n, int with_mtf, uint8_t *const *out,
                        const uint64_t *cap, uint64_t *out_bytes, tc_block_info *info) {
     TC_TRY(tc_ws_reset(ctx));
@@ -560,16 +563,17 @@ int blocks_packed_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nb
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     bool d2h_pending[2] = {false, false};
     int rc_all = TC_OK;
-    auto issue_h2d = [&](uint64_t b) -> int {
-        const int s = (int)(((b - first) / stride) & 1);
+    auto issue_h2d = [&](uint64_t b, int s) -> int {
         if (n[b]) TC_CUDA(cudaMemcpyAsync(d_text[s], text[b], n[b], cudaMemcpyHostToDevice, ctx->s_h2d));
         TC_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d));
         return TC_OK;
     };
-    TC_TRY(issue_h2d(first));
-    for (uint64_t b = first; b < nblocks; b += stride) {
-        const int s = (int)(((b - first) / stride) & 1);
-        if (b + stride < nblocks) TC_TRY(issue_h2d(b + stride));
+    uint64_t b = next.fetch_add(1), b_next;
+    if (b < nblocks) TC_TRY(issue_h2d(b, 0));
+    for (uint64_t k = 0; b < nblocks; b = b_next, k++) {
+        const int s = (int)(k & 1);
+        b_next = next.fetch_add(1);
+        if (b_next < nblocks) TC_TRY(issue_h2d(b_next, s ^ 1)); // that slot's text was consumed by the block before (host-synced)
         TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
         if (d2h_pending[s]) TC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));
         WsMark mk = tc_ws_mark(ctx);
@@ -611,8 +615,8 @@ int blocks_packed_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nb
 } // namespace
 
 namespace {
-// Runs fn(lane context, first block, stride) on `lanes` lanes: lane 0 on the caller's context and
-// thread, the others on child contexts driven by helper threads.  TC_E_CAP from any lane is
+// Runs fn(lane context) on `lanes` lanes: lane 0 on the caller's context and thread, the others on
+// child contexts driven by helper threads.  TC_E_CAP from any lane is
 // reported after all lanes have finished; any other error wins.
 template <class F>
 int run_lanes(tc_ctx *ctx, uint64_t nblocks, F fn) {
@@ -620,15 +624,15 @@ int run_lanes(tc_ctx *ctx, uint64_t nblocks, F fn) {
     if ((uint64_t)lanes > nblocks) lanes = (int)nblocks;
     for (int l = 1; l < lanes; l++)
         if (!ctx->child[l - 1]) TC_TRY(tc_ctx_create(ctx->device, &ctx->child[l - 1]));
-    if (lanes <= 1) return fn(ctx, (uint64_t)0, (uint64_t)1);
+    if (lanes <= 1) return fn(ctx);
     // work queued earlier on the caller's stream (e.g. the producer of device-resident texts) must be
     // visible to the other lanes' streams
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     int rc[tc_ctx::MAX_LANES] = {TC_OK, TC_OK, TC_OK, TC_OK};
     std::thread th[tc_ctx::MAX_LANES - 1];
     for (int l = 1; l < lanes; l++)
-        th[l - 1] = std::thread([&, l] { rc[l] = fn(ctx->child[l - 1], (uint64_t)l, (uint64_t)lanes); });
-    rc[0] = fn(ctx, (uint64_t)0, (uint64_t)lanes);
+        th[l - 1] = std::thread([&, l] { rc[l] = fn(ctx->child[l - 1]); });
+    rc[0] = fn(ctx);
     for (int l = 1; l < lanes; l++) th[l - 1].join();
     int out = TC_OK;
     for (int l = 0; l < lanes; l++) {
@@ -643,7 +647,7 @@ int run_lanes(tc_ctx *ctx, uint64_t nblocks, F fn) {
 }
 } // namespace
 
-// Three lanes by default (TC_B200_LANES = 1..4): block b runs on lane b mod lanes; lane 0 is the caller's
+// Three lanes by default (TC_B200_LANES = 1..4), each taking the next unclaimed block; lane 0 is the caller's
 // context and thread, the others are child contexts driven by helper threads.  Each block's kernel
 // chain has short serial phases (single-CTA scans, two host syncs); with several blocks in flight
 // the other lanes' kernels fill them.
@@ -659,8 +663,9 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
         nmax = n[b] > nmax ? n[b] : nmax;
         out_bytes[b] = 0;
     }
-    return run_lanes(ctx, nblocks, [&](tc_ctx *c, uint64_t first, uint64_t stride) {
-        return blocks_packed_lane(c, first, stride, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
+    std::atomic<uint64_t> next{0};
+    return run_lanes(ctx, nblocks, [&](tc_ctx *c) {
+        return blocks_packed_lane(c, next, nblocks, nmax, text, n, with_mtf, out, cap, out_bytes, info);
     });
 }
 
@@ -668,11 +673,11 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
 // copies; the same lanes as tc_blocks_encode_packed, so the serial phases of one block's
 // kernel chain are filled by the other block's kernels.
 namespace {
-int blocks_dev_lane(tc_ctx *ctx, uint64_t first, uint64_t stride, uint64_t nblocks, const uint8_t *const *d_text,
+int blocks_dev_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, uint64_t nblocks, const uint8_t *const *d_text,
                     const uint64_t *n, int with_mtf, uint32_t *const *d_count, int16_t *const *d_rsym,
                     const uint64_t *cap, tc_block_info *info) {
     int rc_all = TC_OK;
-    for (uint64_t b = first; b < nblocks; b += stride) {
+    for (uint64_t b = next.fetch_add(1); b < nblocks; b = next.fetch_add(1)) {
         TC_TRY(tc_ws_reset(ctx));
         int rc = compress_dev(ctx, d_text[b], n[b], with_mtf != 0, d_count[b], d_rsym[b], cap[b], &info[b]);
         if (rc == TC_E_CAP) rc_all = rc;
@@ -691,8 +696,9 @@ extern "C" int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t
     if (!d_text || !n || !d_count || !d_rsym || !cap || !info) return TC_E_ARG;
     for (uint64_t b = 0; b < nblocks; b++)
         if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
-    return run_lanes(ctx, nblocks, [&](tc_ctx *c, uint64_t first, uint64_t stride) {
-        return blocks_dev_lane(c, first, stride, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
+    std::atomic<uint64_t> next{0};
+    return run_lanes(ctx, nblocks, [&](tc_ctx *c) {
+        return blocks_dev_lane(c, next, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);
     });
 }
 
