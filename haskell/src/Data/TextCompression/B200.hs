@@ -34,6 +34,10 @@ module Data.TextCompression.B200
   , seqFromRLEW8
     -- * composed helpers (device-resident BWT -> MTF -> RLE)
   , bwtMtfRleW8
+    -- * multi-block compression with packed block containers (tc_packed_header, include/tc_b200.h)
+  , compressBlocksPackedW8
+  , unpackBlockW8
+  , decodePackedW8
     -- * Data.FMIndex.Internal replacements
   , B200FM
   , buildFMIndexW8
@@ -54,7 +58,8 @@ import           Foreign.C.String      (CString, peekCString)
 import           Foreign.C.Types       (CInt (..), CSize (..))
 import           Foreign.ForeignPtr    (ForeignPtr, newForeignPtr, withForeignPtr)
 import           Foreign.Marshal.Alloc (alloca)
-import           Foreign.Marshal.Array (peekArray, pokeArray)
+import           Foreign.Marshal.Array (peekArray, pokeArray, withArray)
+import           Foreign.Marshal.Utils (withMany)
 import           Foreign.Ptr           (FunPtr, Ptr, castPtr, nullPtr)
 import           Foreign.Storable      (peek, peekByteOff)
 import           System.IO.Unsafe      (unsafePerformIO)
@@ -274,6 +279,58 @@ bwtMtfRleW8 xs
           cs <- peekArray r pc :: IO [Word32]
           ss <- peekArray r ps :: IO [Int16]
           pure (DS.fromList (zip (map fromIntegral cs) (map fromIntegral ss)))
+
+-- | @fmap bytestringToBWTToMTFB blocks@ + RLE of the index streams, kept compressed: one packed block
+-- container (a strict ByteString: tc_packed_header, then the runs at 2 bytes + 1 bit each) per
+-- input block, in input order.  One call for the whole list: the library overlaps every block's
+-- H2D / D2H copies with the kernels of its neighbours and keeps several blocks in flight.
+compressBlocksPackedW8 :: [BS.ByteString] -> [BS.ByteString]
+compressBlocksPackedW8 []     = []
+compressBlocksPackedW8 blocks = unsafePerformIO $ withB200 $ \ctx -> do
+  let nb = length blocks
+      ns = map (fromIntegral . BS.length) blocks :: [Word64]
+  caps <- mapM c_packed_bound ns
+  outs <- mapM (pinned . fromIntegral) caps :: IO [ForeignPtr Word8]
+  info <- pinned (552 * nb)                                  -- tc_block_info is 552 bytes
+  withMany BSU.unsafeUseAsCStringLen blocks $ \ins ->
+    withMany withForeignPtr outs $ \pouts ->
+      withArray (map (castPtr . fst) ins) $ \ptext ->
+        withArray ns $ \pn -> withArray pouts $ \pout -> withArray caps $ \pcap ->
+          withArray (replicate nb 0) $ \pbytes -> withForeignPtr info $ \pinfo -> do
+            c_blocks_encode_packed ctx (fromIntegral nb) ptext pn 1 pout pcap pbytes pinfo >>= check ctx
+            sizes <- peekArray nb pbytes
+            forM (zip pouts sizes) $ \(po, sz) -> BS.packCStringLen (castPtr po, fromIntegral sz)
+
+-- | Host only (no device): the (count, MTF index or BWT symbol) runs a container holds -- what
+-- `bwtMtfRleW8` returns for the same block.  A symbol of -1 is `Nothing`.
+unpackBlockW8 :: BS.ByteString -> Seq (Int, Int)
+unpackBlockW8 blob = unsafePerformIO $ BSU.unsafeUseAsCStringLen blob $ \(p, len) -> do
+  info <- pinned 552
+  withForeignPtr info $ \pinfo -> do
+    rc0 <- c_packed_unpack (castPtr p) (fromIntegral len) nullPtr nullPtr 0 pinfo   -- header only: R
+    when (rc0 /= 0 && rc0 /= tcECap) $ throwIO (ErrorCall "libtc_b200: malformed block container")
+    r <- fromIntegral <$> (peekByteOff pinfo 544 :: IO Word64)
+    if r == 0 then pure DS.empty else do
+      cnt <- pinned (4 * r)
+      sym <- pinned (2 * r)
+      withForeignPtr cnt $ \pc -> withForeignPtr sym $ \ps -> do
+        rc <- c_packed_unpack (castPtr p) (fromIntegral len) pc ps (fromIntegral r) pinfo
+        when (rc /= 0) $ throwIO (ErrorCall "libtc_b200: malformed block container")
+        cs <- peekArray r pc :: IO [Word32]
+        ss <- peekArray r ps :: IO [Int16]
+        pure (DS.fromList (zip (map fromIntegral cs) (map fromIntegral ss)))
+
+-- | Container -> text, unpacked and decoded on the device (the inverse chain of
+-- bytestringFromBWTFromMTFB / bytestringFromBWTFromRLEB, src/Data/MTF.hs, src/Data/RLE.hs).
+decodePackedW8 :: BS.ByteString -> BS.ByteString
+decodePackedW8 blob = unsafePerformIO $ withB200 $ \ctx ->
+  BSU.unsafeUseAsCStringLen blob $ \(p, len) -> do
+    n <- if len >= 24 then fromIntegral <$> (peekByteOff p 16 :: IO Word64) else pure 0   -- tc_packed_header.n
+    out <- pinned (n + 2)
+    alloca $ \pn -> withForeignPtr out $ \po -> do
+      c_packed_decode ctx (castPtr p) (fromIntegral len) po (fromIntegral (n + 2)) pn >>= check ctx
+      m <- fromIntegral <$> peek pn
+      BS.packCStringLen (castPtr po, m)
 
 -- | Device-resident FM-index handle (tc_fm); freed by the GC finaliser.
 newtype B200FM = B200FM (ForeignPtr TcFm)

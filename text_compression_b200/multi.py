@@ -50,14 +50,17 @@ def blocks_of_rank(n_blocks: int, world_size: int, rank: int):
     return list(range(rank, n_blocks, world_size))
 
 
-def compress_blocks_sharded(texts, with_mtf: bool = True, ctx=None):
+def compress_blocks_sharded(texts, with_mtf: bool = True, ctx=None, packed: bool = False):
     """Config 5 (multi-block compression): this rank compresses blocks rank, rank + world, ...
-    with the pipelined multi-block call (tc_blocks_encode); no data-path collective.  Returns
-    [(block index, CompressedBlock)] for the blocks this rank owns."""
+    with the pipelined multi-block call; no data-path collective.  Returns [(block index, result)]
+    for the blocks this rank owns: CompressedBlock records (tc_blocks_encode), or with
+    packed=True one block container per block (tc_blocks_encode_packed, a third of the bytes
+    over PCIe and several blocks in flight per GPU)."""
     from . import block
     ws, rk = world()
     mine = blocks_of_rank(len(texts), ws, rk)
-    return list(zip(mine, block.compress_blocks([texts[b] for b in mine], with_mtf, ctx)))
+    fn = block.compress_blocks_packed if packed else block.compress_blocks
+    return list(zip(mine, fn([texts[b] for b in mine], with_mtf, ctx)))
 
 
 def query_slice(q: int, world_size: int, rank: int):
