@@ -313,16 +313,16 @@ __global__ void __launch_bounds__(RT)
                     }
                     H = i + 1;
                 }
-                if (owns_last && k == lim - 1) { // end-of-input flush (src/Data/RLE/Internal.hs:125-130)
-                    if (ck >= 0) {
-                        put(o, (uint32_t)N - (H - 1), ck);
-                    } else {
-                        put(o, J == 0 ? 1u : J - H + 1, -1);
-                    }
-                    o += 1;
-                }
                 p = ck;
             }
+        }
+        if (owns_last && lim > 0) { // end-of-input flush (src/Data/RLE/Internal.hs:125-130); p = x[N-1]
+            if (p >= 0) {
+                put(o, (uint32_t)N - (H - 1), p);
+            } else {
+                put(o, J == 0 ? 1u : J - H + 1, -1);
+            }
+            o += 1;
         }
     }
     __syncthreads();
