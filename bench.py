@@ -58,8 +58,8 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+def ncu_row(kernel: str):
+    """{traffic, warp_instructions, issue_active_pct} per launch of `kernel` from the committed
     ncu --set full capture of this workload (profiles/, produced by tools/make_profiles.sh)."""
     import csv
     path = os.path.join(ROOT, "profiles", f"r1e_ncu_full_summary_{ALPHABET}.csv")
@@ -71,10 +71,13 @@ def ncu_traffic(kernel: str):
         for r in rows[2:]:
             if short in r[ix["Kernel Name"]]:
                 ur, uw = rows[1][ix["dram__bytes_read.sum"]], rows[1][ix["dram__bytes_write.sum"]]
-                return float(r[ix["dram__bytes_read.sum"]]) * unit.get(ur, 1.0) + float(r[ix["dram__bytes_write.sum"]]) * unit.get(uw, 1.0)
+                return {"traffic": float(r[ix["dram__bytes_read.sum"]]) * unit.get(ur, 1.0)
+                        + float(r[ix["dram__bytes_write.sum"]]) * unit.get(uw, 1.0),
+                        "warp_instructions": float(r[ix["smsp__inst_executed.sum"]]),
+                        "issue_active_pct": float(r[ix["smsp__issue_active.avg.pct_of_peak_sustained_active"]])}
     except Exception:
         pass
-    return None
+    return {"traffic": None}
 
 
 class ClockSampler(threading.Thread):
@@ -355,7 +358,7 @@ def run_b200(args):
     if tbytes:
         roofline["achieved"] = tbytes / 1e9 / (tms / 1e3)
         roofline["frac"] = roofline["achieved"] / peak
-    roofline["traffic"] = ncu_traffic(tname)
+    roofline.update(ncu_row(tname))   # traffic + the issue-side figures of the same capture (the kernel is issue-bound)
     N = n + 1
 
     def pass_ms(prefixes):
