@@ -136,3 +136,56 @@ def test_packed_container_host_side():
     blob2 = pack_container(3, 4, 0, 0, [], [1, 2, 1], [5, 6, -1], False)
     assert L.tc_packed_unpack(_lib.ptr(blob2), blob2.size, _lib.ptr(cnt1), _lib.ptr(sym1), 1, C.byref(info)) == _lib.TC_E_CAP
     assert info.R == 3
+
+
+def test_header_is_plain_c():
+    """include/tc_b200.h is the drop-in boundary: it must compile as C99 (no C++-isms), and
+    tc_packed_header must have the 640-byte layout the container format states."""
+    import subprocess
+    import tempfile
+    src = ('#include "tc_b200.h"\n#include <stddef.h>\n'
+           'typedef char a1[sizeof(tc_packed_header) == 640 ? 1 : -1];\n'
+           'typedef char a2[offsetof(tc_packed_header, R) == 40 ? 1 : -1];\n'
+           'typedef char a3[offsetof(tc_packed_header, final_list) == 112 ? 1 : -1];\n'
+           'typedef char a4[offsetof(tc_block_info, R) == 544 && sizeof(tc_block_info) == 552 ? 1 : -1];\n'
+           'int main(void) { return tc_packed_bound(0) > 0 ? 0 : 1; }\n')
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "t.c")
+        open(p, "w").write(src)
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I",
+                            os.path.join(ROOT, "include"), p], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_packed_container_fuzz():
+    """tc_packed_unpack against the numpy writer on random run sequences (random counts incl. >= 255,
+    all 258 symbol codes), and on corrupted containers: every outcome is TC_OK or TC_E_ARG/TC_E_CAP,
+    never a crash, and an accepted container unpacks to R runs."""
+    import ctypes as C
+    from tests.util import pack_container
+    from text_compression_b200 import _lib, block
+    L = _lib.load()
+    rng = np.random.default_rng(20261018)
+    for case in range(150):
+        R = int(rng.integers(0, 700))
+        cnt = rng.integers(1, 6, size=R).astype(np.uint32)
+        big = rng.random(R) < 0.03
+        cnt[big] = rng.integers(255, 1 << 31, size=int(big.sum())).astype(np.uint32)
+        sym = rng.integers(-1, 257, size=R).astype(np.int16)
+        with_mtf = bool(case & 1)
+        fin = rng.permutation(np.arange(-1, 256, dtype=np.int16))[: int(rng.integers(0, 258))]
+        blob = pack_container(12345, 12346, 7, len(fin), fin, cnt, sym, with_mtf)
+        got = block.unpack_block(blob)
+        assert np.array_equal(got.counts, cnt) and np.array_equal(got.syms, sym)
+        assert got.final_list.tolist() == fin.tolist() and got.with_mtf == with_mtf and got.primary == 7
+        # corruption: a few random byte flips anywhere (header included)
+        bad = blob.copy()
+        for pos in rng.integers(0, bad.size, size=3):
+            bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        info = _lib.BlockInfo()
+        c = np.empty(R + 8, np.uint32)
+        s = np.empty(R + 8, np.int16)
+        rc = L.tc_packed_unpack(_lib.ptr(bad), bad.size, _lib.ptr(c), _lib.ptr(s), R + 8, C.byref(info))
+        assert rc in (_lib.TC_OK, _lib.TC_E_ARG, _lib.TC_E_CAP)
+        if rc == _lib.TC_OK:
+            assert int(info.R) <= R + 8
