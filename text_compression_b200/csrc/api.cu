@@ -331,7 +331,6 @@ int blocks_streams(tc_ctx *ctx) {
         TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
         TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
     }
-    TC_CUDA(cudaEventCreateWithFlags(&ctx->ev_comp, cudaEventDisableTiming));
     return TC_OK;
 }
 } // namespace

@@ -21,7 +21,7 @@ struct tc_ctx {
     bool own_stream = false;
     // copy streams + events of the batch entry point (created on first use)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr}, ev_comp = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     // Grow-only scratch arena: pointers handed out stay valid until the next ws_reset().
     struct Chunk {
         char *p;

@@ -85,7 +85,6 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
         if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
     }
-    if (ctx->ev_comp) cudaEventDestroy(ctx->ev_comp);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
