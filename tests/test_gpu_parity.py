@@ -487,6 +487,22 @@ def test_device_resident_batch(ctx):
     assert int(info.R) == one.R       # capacity of block 1's buffers is too small: TC_E_CAP, R still reported
 
 
+def test_stream_roundtrip(ctx):
+    """TCZ1 stream (text_compression_b200/stream.py): blocks of a byte string as packed containers --
+    ragged last block, empty input, both chains, a block size that gives many tiny blocks."""
+    from text_compression_b200 import stream
+    data = gen_ascii(21, 100000).tobytes() + gen_acgtn(22, 50001).tobytes() + b"a" * 3000
+    for bs, with_mtf in ((1 << 16, True), (40000, False), (1 << 20, True), (777, True)):
+        z = stream.compress_stream(data, bs, with_mtf, ctx)
+        block_bytes, total, parts = stream.split_stream(z)
+        assert (block_bytes, total, len(parts)) == (bs, len(data), -(-len(data) // bs))
+        if with_mtf:   # the BWT -> RLE chain inherits the reference's Q1 round-trip break on some inputs
+            assert stream.decompress_stream(z, ctx) == data
+    assert stream.decompress_stream(stream.compress_stream(b"", 1024, True, ctx), ctx) == b""
+    with pytest.raises(ValueError):
+        stream.split_stream(z[:-5])
+
+
 def test_q1_trailing_nothing_stream(ctx, orc):
     """Texts that are their own greatest suffix: the reference's RLE re-emits a stale pair (Q1)
     and its own round trip breaks; the GPU stream must equal the oracle's, not round-trip."""

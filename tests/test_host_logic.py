@@ -189,3 +189,19 @@ def test_packed_container_fuzz():
         assert rc in (_lib.TC_OK, _lib.TC_E_ARG, _lib.TC_E_CAP)
         if rc == _lib.TC_OK:
             assert int(info.R) <= R + 8
+
+
+def test_stream_framing_host_side():
+    """TCZ1 framing (no device): split_stream reads what compress_stream's layout states and
+    refuses truncated or foreign input."""
+    import struct
+    from tests.util import pack_container
+    from text_compression_b200 import stream
+    c1 = pack_container(3, 4, 0, 0, [], [1, 2, 1], [5, 6, -1], False).tobytes()
+    c2 = pack_container(0, 0, 0, 0, [], [], [], True).tobytes()
+    z = struct.pack("<4sIQQ", b"TCZ1", 3, 3, 2) + struct.pack("<Q", len(c1)) + c1 + struct.pack("<Q", len(c2)) + c2
+    bs, total, parts = stream.split_stream(z)
+    assert (bs, total, parts) == (3, 3, [c1, c2])
+    for bad in (z[:10], z[:40], b"XXXX" + z[4:], z[:-1]):
+        with pytest.raises(ValueError):
+            stream.split_stream(bad)
