@@ -204,7 +204,7 @@ def run_b200(args):
     for b in range(NBLOCKS):
         d_text[b].copy_(torch.from_numpy(host_blocks[b]))
     cap = n + 3
-    NOUT = 4   # run buffers: blocks in flight never share one (at most 4 lanes)
+    NOUT = 8   # run buffers: blocks in flight (at most 4 lanes, claimed in order) never share one
     d_count = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(NOUT)]
     d_rsym = [torch.empty(cap, dtype=torch.int16, device="cuda") for _ in range(NOUT)]
     torch.cuda.synchronize()
