@@ -695,6 +695,7 @@ int blocks_dev_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, uint64_t nblocks, 
                     const uint64_t *n, int with_mtf, uint32_t *const *d_count, int16_t *const *d_rsym,
                     const uint64_t *cap, tc_block_info *info) {
     int rc_all = TC_OK;
+    TC_CUDA(cudaSetDevice(ctx->device)); // helper threads start on device 0; a lane may find no block left to claim
     for (uint64_t b = next.fetch_add(1); b < nblocks; b = next.fetch_add(1)) {
         TC_TRY(tc_ws_reset(ctx));
         int rc = compress_dev(ctx, d_text[b], n[b], with_mtf != 0, d_count[b], d_rsym[b], cap[b], &info[b]);
