@@ -70,6 +70,7 @@ def lib():
         L.orc_fms_count.argtypes = [vp, vp, C.c_uint64]
         L.orc_fms_count.restype = C.c_int64
         L.orc_fms_count_batch.argtypes = [vp, vp, vp, C.c_uint64, vp, C.c_int]
+        L.orc_naive_search.argtypes = [vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, vp, vp, vp, C.c_uint64, u64p]
         _lib = L
     return _lib
 
@@ -260,6 +261,32 @@ class FMIndexSampled:
                 self._h = C.c_void_p(None)
         except Exception:
             pass
+
+
+# ---- independent occurrence scan (full-size FM-index checks) -------------
+def naive_search(text, pats: np.ndarray, want_pos: bool = False):
+    """Brute-force occurrences of q equal-length patterns (rows of `pats`) in `text`:
+    counts int64[q] and, with want_pos, (hit_off uint64[q+1], 1-based positions ascending per pattern).
+    Not a restatement of the reference: the definition count / locate must agree with (patterns over
+    symbols that occur in the text)."""
+    t = _u8(text)
+    p = np.ascontiguousarray(pats, dtype=np.uint8)
+    q, m = p.shape
+    cnt = np.empty(q, dtype=np.int64)
+    tot = C.c_uint64(0)
+    if not want_pos:
+        _check(lib().orc_naive_search(_p(t), t.size, _p(p), q, m, _p(cnt), None, None, 0, C.byref(tot)))
+        return cnt
+    ho = np.empty(q + 1, dtype=np.uint64)
+    cap = 1 << 20
+    while True:
+        pos = np.empty(cap, dtype=np.uint64)
+        rc = lib().orc_naive_search(_p(t), t.size, _p(p), q, m, _p(cnt), _p(ho), _p(pos), cap, C.byref(tot))
+        if rc == ORC_E_CAP:
+            cap = int(tot.value) + 1
+            continue
+        _check(rc)
+        return cnt, ho, pos[: tot.value].copy()
 
 
 # ---- Seq-level renderings used by the golden tests -----------------------

@@ -595,3 +595,112 @@ int orc_fms_count_batch(const orc_fms *fm, const uint8_t *pats, const uint64_t *
     free(jobs);
     return ORC_OK;
 }
+
+/* ------------------------------------------------------------------ */
+/* Independent occurrence scan (NOT a restatement of the reference):   */
+/* the definition countFMIndex / locateFMIndex must agree with at the  */
+/* BASELINE sizes (100 Mbp / 1 Gbp), where the dense reference tables  */
+/* cannot be built.  For q patterns of one length m: every text        */
+/* position whose m symbols equal the pattern, by a rolling hash over  */
+/* the text, a hash table of the patterns and a memcmp on every hash   */
+/* hit.  count[i] = occurrences of pattern i; when pos != NULL the     */
+/* 1-based start positions of pattern i, ascending, are                */
+/* pos[hit_off[i] .. hit_off[i+1]) (hit_off has q+1 entries; *total is */
+/* the number of hits, TC-style: more than cap gives ORC_E_CAP).       */
+/* Agreement holds for patterns made of symbols that occur in the text */
+/* (quirk Q4 of the reference, SURVEY.md 2.3, concerns absent ones).   */
+/* ------------------------------------------------------------------ */
+typedef struct {
+    uint64_t pos;
+    uint32_t pat;
+} ns_hit;
+static int ns_hit_cmp(const void *a, const void *b) {
+    const ns_hit *x = (const ns_hit *)a, *y = (const ns_hit *)b;
+    if (x->pat != y->pat) return x->pat < y->pat ? -1 : 1;
+    return x->pos < y->pos ? -1 : (x->pos > y->pos);
+}
+int orc_naive_search(const uint8_t *t, uint64_t n, const uint8_t *pats, uint64_t q, uint64_t m, int64_t *count,
+                     uint64_t *hit_off, uint64_t *pos, uint64_t cap, uint64_t *total) {
+    const uint64_t B = 0x9E3779B97F4A7C15ull | 1ull;
+    for (uint64_t i = 0; i < q; i++) count[i] = 0;
+    if (total) *total = 0;
+    if (hit_off) memset(hit_off, 0, (q + 1) * sizeof(uint64_t));
+    if (m == 0 || m > n || q == 0) return ORC_OK;
+    uint64_t tsize = 16;
+    while (tsize < 4 * q) tsize <<= 1;
+    /* table slot -> first pattern with that content; same[] chains identical patterns */
+    uint32_t *slot = (uint32_t *)malloc(tsize * sizeof(uint32_t));
+    uint64_t *hk = (uint64_t *)malloc(q * sizeof(uint64_t));
+    uint32_t *same = (uint32_t *)malloc(q * sizeof(uint32_t));
+    if (!slot || !hk || !same) return ORC_E_NOMEM;
+    memset(slot, 0xff, tsize * sizeof(uint32_t));
+    for (uint64_t i = 0; i < q; i++) {
+        uint64_t h = 0;
+        for (uint64_t j = 0; j < m; j++) h = h * B + pats[i * m + j] + 1;
+        hk[i] = h;
+        same[i] = 0xffffffffu;
+        uint64_t s = (h ^ (h >> 29)) & (tsize - 1);
+        for (;;) {
+            if (slot[s] == 0xffffffffu) {
+                slot[s] = (uint32_t)i;
+                break;
+            }
+            uint32_t f = slot[s];
+            if (hk[f] == h && memcmp(pats + (uint64_t)f * m, pats + i * m, m) == 0) { /* duplicate pattern */
+                same[i] = same[f];
+                same[f] = (uint32_t)i;
+                break;
+            }
+            s = (s + 1) & (tsize - 1);
+        }
+    }
+    uint64_t Bm = 1; /* B^(m-1) */
+    for (uint64_t j = 1; j < m; j++) Bm *= B;
+    uint64_t nh = 0, hcap = 1 << 16;
+    ns_hit *hits = pos ? (ns_hit *)malloc(hcap * sizeof(ns_hit)) : NULL;
+    uint64_t h = 0;
+    for (uint64_t j = 0; j < m; j++) h = h * B + t[j] + 1;
+    for (uint64_t i = 0;; i++) {
+        uint64_t s = (h ^ (h >> 29)) & (tsize - 1);
+        while (slot[s] != 0xffffffffu) {
+            uint32_t f = slot[s];
+            if (hk[f] == h && memcmp(pats + (uint64_t)f * m, t + i, m) == 0) {
+                for (uint32_t p = f; p != 0xffffffffu; p = same[p]) {
+                    count[p]++;
+                    if (hits) {
+                        if (nh == hcap) {
+                            hcap *= 2;
+                            hits = (ns_hit *)realloc(hits, hcap * sizeof(ns_hit));
+                            if (!hits) return ORC_E_NOMEM;
+                        }
+                        hits[nh].pos = i + 1;
+                        hits[nh].pat = p;
+                    }
+                    nh++;
+                }
+                break;
+            }
+            s = (s + 1) & (tsize - 1);
+        }
+        if (i + m >= n) break;
+        h = (h - (uint64_t)(t[i] + 1) * Bm) * B + t[i + m] + 1;
+    }
+    if (total) *total = nh;
+    int rc = ORC_OK;
+    if (hits) {
+        qsort(hits, nh, sizeof(ns_hit), ns_hit_cmp);
+        uint64_t o = 0;
+        for (uint64_t i = 0; i < q; i++) {
+            hit_off[i] = o;
+            o += (uint64_t)count[i];
+        }
+        hit_off[q] = o;
+        if (nh > cap) rc = ORC_E_CAP;
+        for (uint64_t k = 0; k < nh && k < cap; k++) pos[k] = hits[k].pos;
+        free(hits);
+    }
+    free(slot);
+    free(hk);
+    free(same);
+    return rc;
+}

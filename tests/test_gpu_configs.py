@@ -1,0 +1,214 @@
+"""GPU parity at the BASELINE.json config sizes: the CUDA path (through the C ABI) against the CPU
+oracle on the exact seeded blocks SURVEY.md 8d names -- every output array compared element for
+element (primary, BWT, MTF indices, the FINAL list in order, run counts and run symbols), not through
+a round trip.  The oracle needs ~11 s per 16 MiB block.  Run on the B200 box with `-m gpu`."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from tests.util import gen_acgtn, gen_ascii, gen_bytes, gen_reads
+
+pytestmark = pytest.mark.gpu
+
+BLOCK = 16 << 20
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from text_compression_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _digest(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _same(name, got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (name, got.shape, want.shape)
+    if not np.array_equal(got, want):
+        bad = np.nonzero(got != want)[0]
+        raise AssertionError((name, "first mismatches at", bad[:5].tolist(), got[bad[:5]].tolist(),
+                              want[bad[:5]].tolist(), "of", int(bad.size)))
+    assert _digest(got.astype(np.int64)) == _digest(want.astype(np.int64))
+
+
+def _check_block(ctx, orc, text, both_chains=True):
+    """One block through every stage of both chains, each stage compared with the oracle."""
+    from text_compression_b200 import block
+    from text_compression_b200._lib import ptr
+    n = text.size
+    N = n + 1
+    # oracle: createSuffixArray/saToBWT, seqToMTF, seqToRLE (oracle/tc_oracle.c)
+    o_bwt = orc.bwt_encode(text)
+    o_primary = int(np.nonzero(o_bwt < 0)[0][0])
+    o_idx, o_fin = orc.mtf_encode(o_bwt)
+    o_cnt, o_sym = orc.rle_encode(o_idx.astype(np.int16))
+    # stage by stage through the C ABI
+    bwt = np.empty(N, dtype=np.uint8)
+    primary = C.c_uint64(0)
+    ctx.call("tc_bwt_encode", ptr(text), n, ptr(bwt), C.byref(primary), None)
+    assert primary.value == o_primary
+    g = bwt.astype(np.int16)
+    g[o_primary] = -1
+    _same("bwt", g, o_bwt)
+    idx = np.empty(N, dtype=np.uint16)
+    fin = np.empty(257, dtype=np.int16)
+    sigma = C.c_uint32(0)
+    ctx.call("tc_mtf_encode_u8", ptr(bwt), N, o_primary, ptr(idx), ptr(fin), C.byref(sigma))
+    assert sigma.value == o_fin.size
+    _same("mtf final list (in order)", fin[: sigma.value], o_fin)
+    _same("mtf indices", idx, o_idx)
+    # the composite the bench times (device-resident chaining), records out
+    blk = block.compress_bwt_mtf_rle(text, ctx)
+    assert blk.primary == o_primary and blk.sigma == o_fin.size
+    _same("composite final list", blk.final_list, o_fin)
+    _same("composite run counts", blk.counts, o_cnt)
+    _same("composite run symbols", blk.syms, o_sym)
+    # run maximality, stated directly: no two neighbouring runs carry the same symbol
+    assert not np.any(blk.syms[1:] == blk.syms[:-1])
+    assert int(blk.counts.sum(dtype=np.uint64)) == N
+    # packed container of the same block (the e2e output of the bench) unpacks to the same records
+    blob = block.compress_blocks_packed([text], True, ctx)[0]
+    u = block.unpack_block(blob)
+    _same("container run counts", u.counts, o_cnt)
+    _same("container run symbols", u.syms, o_sym)
+    _same("container final list", u.final_list, o_fin)
+    if both_chains:   # bytestringToBWTToRLEB: runs over the BWT symbols incl. Nothing
+        r_cnt, r_sym = orc.rle_encode(o_bwt)
+        blk2 = block.compress_bwt_rle(text, ctx)
+        _same("bwt->rle counts", blk2.counts, r_cnt)
+        _same("bwt->rle symbols", blk2.syms, r_sym)
+    # and back
+    assert block.decompress(blk, ctx) == text.tobytes()
+
+
+def test_c2_random_byte_block_vs_oracle(ctx, orc):
+    """BASELINE config 2, the block bench.py times: gen_bytes(0xC2, 16 MiB), sigma = 257."""
+    _check_block(ctx, orc, gen_bytes(0xC2, BLOCK))
+
+
+def test_c2_text_block_vs_oracle(ctx, orc):
+    """BASELINE config 2, Text variant: 16 MiB printable ASCII (seed 0xC2B), through the Text API too."""
+    text = gen_ascii(0xC2B, BLOCK)
+    _check_block(ctx, orc, text)
+    from text_compression_b200 import mtf as M
+    s = text[: 1 << 20].tobytes().decode("ascii")
+    m = M.textToBWTToMTFT(s, ctx)
+    o_idx, o_fin = orc.mtf_encode(orc.bwt_encode(text[: 1 << 20]))
+    _same("textToBWTToMTFT indices", m.indices, o_idx)
+    _same("textToBWTToMTFT final list", m.final_list.codes, o_fin)
+
+
+def test_c5_acgtn_block_vs_oracle(ctx, orc):
+    """BASELINE config 5: one 16 MiB ACGTN block (seed 0xC5), sigma = 6 (the register-list MTF path)."""
+    _check_block(ctx, orc, gen_acgtn(0xC5, BLOCK))
+
+
+def test_lsd_path_32mi_vs_oracle(ctx, orc):
+    """> 25 Mi symbols takes the LSD + prefix-doubling suffix sort -- the path that builds the C3 / C4
+    indices.  32 Mi ACGTN: SA and BWT against the oracle."""
+    from text_compression_b200._lib import ptr
+    text = gen_acgtn(0xC5 + 7, 32 << 20)
+    n = text.size
+    o_bwt, o_sa = orc.bwt_encode(text, want_sa=True)
+    bwt = np.empty(n + 1, dtype=np.uint8)
+    sa = np.empty(n + 1, dtype=np.uint32)
+    primary = C.c_uint64(0)
+    ctx.call("tc_bwt_encode", ptr(text), n, ptr(bwt), C.byref(primary), ptr(sa))
+    _same("suffix array", sa, o_sa)
+    g = bwt.astype(np.int16)
+    g[primary.value] = -1
+    _same("bwt", g, o_bwt)
+
+
+def _check_fm_full(ctx, orc, n, q, m, rate, seed):
+    """Index over n bp of synthetic ACGTN; q sampled reads of m bp (10 % with a substitution) against an
+    independent occurrence scan of the text (oracle.naive_search): counts, the located positions as
+    sets, and the SA-rank order of every multi-hit pattern by comparing the located suffixes."""
+    from text_compression_b200 import fmindex
+    step = 100_000_000
+    text = np.concatenate([gen_acgtn(seed + 1000 * i, min(step, n - o)) for i, o in enumerate(range(0, n, step))])
+    fm = fmindex.FMIndex(text, "B", rate, ctx)
+    assert int(fm.info.N) == n + 1 and int(fm.info.sigma) == 6   # $ACGNT
+    reads = gen_reads(seed + 1, text, q, m)
+    # short patterns too: 12-mers have ~n / 4^12 occurrences each, which exercises multi-hit locate
+    shorts = gen_reads(seed + 2, text, 64, 12, mut_frac=0.0)
+    for pats in (reads, shorts):
+        cnt, ho, pos = orc.naive_search(text, pats, want_pos=True)
+        got = fm.count_many([p.tobytes() for p in pats])
+        want = np.where(cnt > 0, cnt, -1)   # countFMIndex: Nothing when there is no occurrence
+        _same("count", got, want)
+        gho, gpos = fm.locate_many([p.tobytes() for p in pats])
+        _same("hit offsets", gho, ho)
+        mm = pats.shape[1]
+        for i in range(pats.shape[0]):
+            a = gpos[int(gho[i]):int(gho[i + 1])].astype(np.int64)
+            b = pos[int(ho[i]):int(ho[i + 1])].astype(np.int64)
+            assert np.array_equal(np.sort(a), b), (i, a[:8], b[:8])
+            # SA-rank order (src/Data/FMIndex.hs:473-474): located suffixes ascend lexicographically
+            for x, y in zip(a[:-1].tolist()[:64], a[1:].tolist()[:64]):
+                sx, sy = text[x - 1: x - 1 + mm + 256].tobytes(), text[y - 1: y - 1 + mm + 256].tobytes()
+                assert sx < sy, (i, x, y)
+    fm.close()
+
+
+def test_c3_full_size_count_and_locate(ctx, orc):
+    """BASELINE config 3 at full size: 100 Mbp reference, 10,000 sampled 100-bp reads, SA rate 32."""
+    _check_fm_full(ctx, orc, 100_000_000, 10_000, 100, 32, 0xC3)
+
+
+def test_c4_full_size_locate(ctx, orc):
+    """BASELINE config 4 at full size: 1 Gbp reference (LSD + doubling build), 2,000 32-bp patterns."""
+    import os
+    if os.environ.get("TC_TEST_SKIP_C4") == "1":
+        pytest.skip("TC_TEST_SKIP_C4=1")
+    _check_fm_full(ctx, orc, 1_000_000_000, 2_000, 32, 32, 0xC4)
+
+
+def test_mtf_kernels_agree(ctx, orc):
+    """The thread-per-chunk MTF encoder (default) and the warp-per-chunk one (TC_B200_MTF_V2=1) against the
+    oracle on skewed, run-heavy and uniform streams over alphabets of 9..257 symbols."""
+    import os
+    from text_compression_b200 import _lib
+    from text_compression_b200._lib import ptr
+    os.environ["TC_B200_MTF_V2"] = "1"
+    try:
+        ctx2 = _lib.Context(0)
+    finally:
+        del os.environ["TC_B200_MTF_V2"]
+    rng = np.random.default_rng(77)
+    for n in (1, 31, 32, 33, 735, 736, 737, 4097, 70001, 1_000_003, 3_000_000):
+        for sigma, mode in ((9, "uniform"), (40, "skew"), (96, "runs"), (200, "skew"), (256, "uniform"), (256, "runs")):
+            alpha = rng.choice(256, size=sigma, replace=False).astype(np.uint8)
+            if mode == "uniform":
+                b = alpha[rng.integers(0, sigma, size=n)]
+            elif mode == "skew":   # what the BWT of real text looks like: a few symbols dominate locally
+                b = alpha[np.minimum(rng.geometric(0.3, size=n) - 1, sigma - 1)]
+            else:
+                reps = rng.integers(1, 40, size=n // 8 + 1)
+                b = np.repeat(alpha[rng.integers(0, sigma, size=reps.size)], reps)[:n]
+            b = np.ascontiguousarray(b)
+            for primary in sorted({0, n // 3, n - 1, n + 9}):
+                x = b.astype(np.int16)
+                if primary < n:
+                    x[primary] = -1
+                o_idx, o_fin = orc.mtf_encode(x)
+                for c in (ctx, ctx2):
+                    idx = np.empty(n, dtype=np.uint16)
+                    fin = np.empty(257, dtype=np.int16)
+                    sg = C.c_uint32(0)
+                    c.call("tc_mtf_encode_u8", ptr(b), n, primary, ptr(idx), ptr(fin), C.byref(sg))
+                    _same(f"indices n={n} sigma={sigma} {mode} primary={primary}", idx, o_idx)
+                    _same("final list", fin[: sg.value], o_fin)
+    ctx2.close()

@@ -47,6 +47,10 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     ctx->sm_count = prop.multiProcessorCount;
     const char *nm = getenv("TC_B200_NO_MSD");
     ctx->no_msd = nm && nm[0] == '1';
+    const char *m2 = getenv("TC_B200_MTF_V2");
+    ctx->mtf_v2 = m2 && m2[0] == '1';
+    const char *ml = getenv("TC_B200_MTF_L");
+    if (ml) ctx->mtf_L = (uint32_t)atoi(ml);
     const char *ln = getenv("TC_B200_LANES");
     if (ln && ln[0] >= '1' && ln[0] <= '0' + tc_ctx::MAX_LANES) ctx->lanes = ln[0] - '0';
     if (have_stream) {

@@ -35,6 +35,21 @@ struct Lut {
 struct SrcU8 {
     const uint8_t *p;
     uint64_t primary;
+    struct Raw {
+        uint4 v;
+    };
+    __device__ __forceinline__ Raw load_raw(uint64_t base) const { return Raw{__ldg(reinterpret_cast<const uint4 *>(p + base))}; }
+    __device__ __forceinline__ void decode_li(const Raw &r, uint64_t base, uint32_t *li) const { // 256 = Nothing, else the byte
+        const uint4 v = r.v;
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) li[k] = (w[k >> 2] >> ((k & 3) * 8)) & 0xff;
+        if (primary - base < 16) {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (base + k == primary) li[k] = 256u;
+        }
+    }
     __device__ __forceinline__ int at(uint64_t i) const { return i == primary ? 0 : (int)p[i] + 1; }
     __device__ __forceinline__ bool can_vec(uint64_t base) const {
         return (reinterpret_cast<uintptr_t>(p + base) & 15) == 0;
@@ -53,6 +68,27 @@ struct SrcU8 {
 };
 struct SrcI16 {
     const int16_t *p;
+    struct Raw {
+        uint4 v[2];
+    };
+    __device__ __forceinline__ Raw load_raw(uint64_t base) const {
+        Raw r;
+        r.v[0] = __ldg(reinterpret_cast<const uint4 *>(p + base));
+        r.v[1] = __ldg(reinterpret_cast<const uint4 *>(p + base + 8));
+        return r;
+    }
+    __device__ __forceinline__ void decode_li(const Raw &r, uint64_t, uint32_t *li) const { // 256 = Nothing, else the byte
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint4 v = r.v[q];
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                int s = (int)(int16_t)((w[k >> 1] >> ((k & 1) * 16)) & 0xffff);
+                li[q * 8 + k] = s < 0 ? 256u : (uint32_t)(s & 0xff);
+            }
+        }
+    }
     __device__ __forceinline__ int at(uint64_t i) const {
         int v = p[i];
         return v < 0 ? 0 : (v & 0xff) + 1;
@@ -235,8 +271,22 @@ struct WarpPro {
     uint32_t okey[VSMAX];
     uint32_t ocount;
 };
+// General form: entry i of a lane is live iff valid[i]; never-seen entries keep the order of ord[i].
+__device__ __forceinline__ void list_positions_g(const uint32_t *tvals, const bool *valid, const uint32_t *ord,
+                                                 uint64_t start, WarpPro &P, uint32_t *posv);
 __device__ __forceinline__ void list_positions(const uint32_t *tvals, uint64_t start, uint32_t sigma, WarpPro &P,
                                                uint32_t *posv) {
+    bool valid[9];
+    uint32_t ord[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        ord[i] = lane_id() + 32 * i;
+        valid[i] = ord[i] < sigma;
+    }
+    list_positions_g(tvals, valid, ord, start, P, posv);
+}
+__device__ __forceinline__ void list_positions_g(const uint32_t *tvals, const bool *valid, const uint32_t *ord,
+                                                 uint64_t start, WarpPro &P, uint32_t *posv) {
     const unsigned lane = lane_id();
     P.win[lane] = 0;
     P.win[lane + 32] = 0;
@@ -245,11 +295,10 @@ __device__ __forceinline__ void list_positions(const uint32_t *tvals, uint64_t s
     uint32_t key[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        uint32_t c = lane + 32 * i;
         uint32_t T = tvals[i];
         // distance back to the last occurrence (>= 1); never-seen ranks sort after every seen one
-        key[i] = T ? (uint32_t)(start - (T - 1)) : (0x80000000u + c);
-        if (c < sigma && key[i] <= WIN_WORDS * 32) atomicOr(&P.win[(key[i] - 1) >> 5], 1u << ((key[i] - 1) & 31));
+        key[i] = T ? (uint32_t)(start - (T - 1)) : (0x80000000u + ord[i]);
+        if (valid[i] && key[i] <= WIN_WORDS * 32) atomicOr(&P.win[(key[i] - 1) >> 5], 1u << ((key[i] - 1) & 31));
     }
     __syncwarp();
     // prefix popcounts of the window, two words per lane
@@ -261,8 +310,7 @@ __device__ __forceinline__ void list_positions(const uint32_t *tvals, uint64_t s
     // collect the keys outside the window
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        uint32_t c = lane + 32 * i;
-        bool out = c < sigma && key[i] > WIN_WORDS * 32;
+        bool out = valid[i] && key[i] > WIN_WORDS * 32;
         unsigned m = __ballot_sync(TC_FULL, out);
         uint32_t base = P.ocount;
         __syncwarp();
@@ -273,9 +321,8 @@ __device__ __forceinline__ void list_positions(const uint32_t *tvals, uint64_t s
     uint32_t m_out = P.ocount;
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        uint32_t c = lane + 32 * i;
         uint32_t p = 0;
-        if (c < sigma) {
+        if (valid[i]) {
             if (key[i] <= WIN_WORDS * 32) {
                 uint32_t b = key[i] - 1;
                 p = P.pre[b >> 5] + __popc(P.win[b >> 5] & ((1u << (b & 31)) - 1));
@@ -422,6 +469,462 @@ __global__ void __launch_bounds__(32)
     for (int i = 0; i < 9; i++) {
         uint32_t c = lane + 32 * i;
         if (c < sigma) final_list[pv[i]] = (uint16_t)c;
+    }
+}
+
+// ---- encode v3: thread per chunk -------------------------------------------------------------
+// The warp-per-chunk replay above spends 342 warp instructions per 32 symbols resolving the
+// dependencies between the 32 positions of a step.  Here every THREAD replays its own chunk,
+// one symbol after the other, so a warp advances 32 chunks per step and nothing has to be
+// resolved across lanes.  Per thread, in shared memory (word-interleaved across the CTA, so
+// any per-thread index is conflict-free):
+//   last[c]   u16: time slot of the latest occurrence of code c (indexed by lidx(c))
+//   bits[32]  one bit per time slot (288 virtual slots for the incoming order + one per
+//             position of the chunk, at most 1024): set = latest occurrence of its code
+//   sfx[g]    8 bytes per group of 8 words: byte k = live bits in words k+1..7 of the group
+// and in registers T (4 x u16: live bits in the groups above g) and the bitmap word that is
+// still being appended to.  MTF index of c = live bits above last[c] = one popcount + one
+// byte of sfx + one field of T: ~50 instructions per symbol per thread, i.e. ~50 warp
+// instructions per 32 symbols.
+constexpr int R3_VS = 288;                              // virtual slots (a multiple of 32)
+constexpr int R3_LMAX = 736;                            // R3_VS + L <= 1024 slots
+constexpr int R3_LASTW = 129;                           // u16 pairs for 257 codes (+1 pad)
+constexpr int R3_BITW = 32;
+constexpr int R3_SFXW = 8;                              // 4 groups x 8 bytes
+constexpr int R3_WORDS = R3_LASTW + R3_BITW + R3_SFXW;  // 169 words = 676 B per thread
+constexpr int R3_CT = 160;                              // threads per CTA: two CTAs per SM
+constexpr int R3_ROW = 288;                             // u16 entries per start row (576 B, 16-byte multiple)
+
+__device__ __forceinline__ uint32_t ldg_u16(const uint16_t *p) { // zero-extended straight into a 32-bit register
+    uint32_t r;
+    asm volatile("ld.global.u16 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t x, uint32_t s) { // x >> s, 0 for s >= 32
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+    return r;
+}
+// code (0 = Nothing, 1 + byte) -> index into last[]: bytes at 0..255, Nothing at 256
+__device__ __forceinline__ uint32_t r3_lidx(uint32_t code) { return code == 0 ? 256u : code - 1u; }
+
+// A tile = the 32 consecutive chunks one warp replays (thread t <-> chunk 32 * tile + t).
+//   T1  per tile: last occurrence (global position + 1) of every code inside the tile
+//   T2  exclusive max-scan of those rows over the tiles; the total gives the FINAL list
+//   T3  per tile: incoming list order from the scanned row, then the order at the start of each of
+//       its 32 chunks: chunk t moves its codes to the front in the order of their last occurrence q
+//       inside the chunk, i.e. every code gets the key  L - q  (seen)  or  L + old position
+//       (not seen) and its new position is the number of smaller keys -- a 1024-bit map of the keys,
+//       one word per lane, and its prefix popcounts.  Written as "start rows" (slot of every code)
+//       that the replay kernel loads.
+// State is indexed by li = r3_lidx(code) throughout; lane l owns li = l, l + 32, ... (no alphabet ranks:
+// the replay never needs them).  present.w[i] bit l <=> li = l + 32 i occurs in the input.
+struct Present {
+    uint32_t w[9];
+};
+constexpr int TP_RLW = 131; // words per row of q values (257 u16 entries; odd, so rows start in different banks)
+
+// q[t][li] = 1 + offset of the last occurrence of li inside chunk t of the tile (0 = none), t = lane
+template <class Src>
+__device__ __forceinline__ void tile_positions(const Src &src, uint64_t N, uint32_t L, uint64_t nchunks, uint64_t tile,
+                                               uint32_t *rows) {
+    const unsigned lane = lane_id();
+    for (int j = lane; j < 32 * TP_RLW; j += 32) rows[j] = 0;
+    __syncwarp();
+    const uint64_t k = tile * 32 + lane;
+    if (k < nchunks) { // forward pass over the own chunk: later positions overwrite earlier ones
+        uint16_t *row = reinterpret_cast<uint16_t *>(rows) + lane * (2 * TP_RLW);
+        const uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+        uint64_t pos = beg;
+        if (src.can_vec(beg)) {
+            // each lane streams its own chunk: keep 64 symbols' worth of loads in flight per lane
+            const uint64_t vend = beg + ((end - beg) & ~63ull);
+            for (; pos < vend; pos += 64) {
+                typename Src::Raw raw[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) raw[b] = src.load_raw(pos + 16 * b);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    uint32_t li[16];
+                    src.decode_li(raw[b], pos + 16 * b, li);
+                    const uint32_t o = (uint32_t)(pos - beg) + 16 * b + 1;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) row[li[j]] = (uint16_t)(o + j);
+                }
+            }
+        }
+        for (; pos < end; pos++) row[r3_lidx((uint32_t)src.at(pos))] = (uint16_t)(pos - beg + 1);
+    }
+    __syncwarp();
+}
+
+constexpr int T1_WARPS = 1; // one tile per CTA: 1,366 tiles of a 16 MiB block spread evenly over the SMs
+// T1 also leaves q[t][li] in the chunk's start row (global memory): T3 reads it from there and replaces it
+// by the slot, so the symbols are scanned once for both.
+template <class Src>
+__global__ void __launch_bounds__(T1_WARPS * 32)
+    mtf3_tile_last_kernel(Src src, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t *__restrict__ trow,
+                          uint16_t *__restrict__ start, uint32_t *__restrict__ scan_ticket) {
+    extern __shared__ __align__(16) uint32_t smt1[];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scan_ticket = 0; // for T2's "last CTA" election
+    const unsigned lane = lane_id();
+    const uint64_t tile = (uint64_t)blockIdx.x * T1_WARPS + (threadIdx.x >> 5);
+    if (tile * 32 >= nchunks) return;
+    uint32_t *rows = smt1 + (threadIdx.x >> 5) * (32 * TP_RLW);
+    tile_positions(src, N, L, nchunks, tile, rows);
+    const uint16_t *q16 = reinterpret_cast<const uint16_t *>(rows);
+    const uint64_t tbase = tile * 32 * L;
+    const uint32_t nt = (uint32_t)(nchunks - tile * 32 < 32 ? nchunks - tile * 32 : 32);
+    uint32_t last[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) last[i] = 0;
+#pragma unroll 2
+    for (uint32_t t = 0; t < nt; t++) {
+        uint16_t *out = start + (tile * 32 + t) * R3_ROW;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const uint32_t li = lane + 32 * i;
+            const uint32_t q = li < SIGMAX ? q16[t * (2 * TP_RLW) + li] : 0u;
+            out[li] = (uint16_t)q;
+            if (q) last[i] = (t << 10) | q; // chunks ascend: the last one that saw the code wins
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+        trow[tile * R3_ROW + lane + 32 * i] =
+            last[i] ? (uint32_t)(tbase + (uint64_t)(last[i] >> 10) * L + (last[i] & 1023u)) : 0u;
+}
+
+// final list = codes by descending last occurrence (li space; the host maps li -> symbol)
+__device__ __forceinline__ void final_list_from(const uint32_t *finalocc, const Present &present, uint64_t N, WarpPro &pro,
+                                                uint16_t *__restrict__ final_list) {
+    const unsigned lane = lane_id();
+    uint32_t tv[9], pv[9], ord[9];
+    bool valid[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const uint32_t li = lane + 32 * i;
+        valid[i] = (present.w[i] >> lane) & 1u;
+        ord[i] = li == 256 ? 0u : li + 1u; // alphabet order: Nothing first
+        tv[i] = valid[i] ? finalocc[li] : 0;
+    }
+    list_positions_g(tv, valid, ord, N, pro, pv);
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+        if (valid[i]) final_list[pv[i]] = (uint16_t)(lane + 32 * i);
+}
+
+// T2: exclusive running max over the tiles for every column.  The tiles are cut into T2_SEGS segments; CTA
+// (column group, segment) scans its segment in place (exclusive, from 0) and publishes the segment total; the CTA
+// that finishes last turns the totals into exclusive segment prefixes (segpre) + finalocc (the final list is
+// ranked from it by one extra warp of the T3 launch, off the critical path).  A consumer takes max(trow[tile][li], segpre[segment of tile][li]).
+constexpr int T2_SEGS = 16;
+constexpr int T2_WARPS = 8;
+__global__ void __launch_bounds__(T2_WARPS * 32)
+    mtf3_tile_scan_kernel(uint32_t *__restrict__ trow, uint64_t ntiles, uint32_t seg_tiles, uint32_t *__restrict__ segpre,
+                          uint32_t *__restrict__ finalocc, uint32_t *__restrict__ scan_ticket) {
+    __shared__ uint32_t part[T2_WARPS][33];
+    __shared__ uint32_t s_last;
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const uint32_t col = blockIdx.x * 32 + lane;
+    const uint64_t s0 = (uint64_t)blockIdx.y * seg_tiles, s1 = s0 + seg_tiles < ntiles ? s0 + seg_tiles : ntiles;
+    const uint64_t per = (seg_tiles + T2_WARPS - 1) / T2_WARPS; // <= 16 up to 64 MiB: one batch of loads per warp
+    const uint64_t t0 = s0 + (uint64_t)w * per < s1 ? s0 + (uint64_t)w * per : s1, t1 = t0 + per < s1 ? t0 + per : s1;
+    uint32_t mx = 0;
+    for (uint64_t tb = t0; tb < t1; tb += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = tb + q < t1 ? trow[(tb + q) * R3_ROW + col] : 0u;
+#pragma unroll
+        for (int q = 0; q < 16; q++) mx = max(mx, v[q]);
+    }
+    part[w][lane] = mx;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int ww = 0; ww < w; ww++) run = max(run, part[ww][lane]);
+    for (uint64_t tb = t0; tb < t1; tb += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = tb + q < t1 ? trow[(tb + q) * R3_ROW + col] : 0u;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            if (tb + q < t1) trow[(tb + q) * R3_ROW + col] = run;
+            run = max(run, v[q]);
+        }
+    }
+    if (w == T2_WARPS - 1) segpre[(uint64_t)blockIdx.y * R3_ROW + col] = run; // the segment's total for now
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(scan_ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence(); // every CTA's totals are visible: this CTA finishes the job, one column per thread
+    for (uint32_t c = threadIdx.x; c < R3_ROW; c += T2_WARPS * 32) {
+        uint32_t tot[T2_SEGS];
+#pragma unroll
+        for (int sg = 0; sg < T2_SEGS; sg++) tot[sg] = __ldcg(&segpre[sg * R3_ROW + c]);
+        uint32_t r = 0;
+#pragma unroll
+        for (int sg = 0; sg < T2_SEGS; sg++) {
+            segpre[sg * R3_ROW + c] = r;
+            r = max(r, tot[sg]);
+        }
+        finalocc[c] = r;
+    }
+}
+
+// T3: start rows.  Warp per tile; lane l owns entries li = l + 32 i, i < 9.  All 288 entries take part
+// in every step (entries that are not codes of the input sit behind the sigma real ones and stay
+// there), so the step has no predicates.
+constexpr int T3_WARPS = 1; // as T1
+struct StartsWarp {
+    uint32_t map8[2][256]; // the key map of a step, one BYTE per key (plain stores; shared-memory atomics cost 2 cycles
+                           // per lane and were the whole kernel), double buffered
+    uint2 wp[32];          // the same map as bits: .x = one word per lane, .y = its exclusive prefix popcount
+    WarpPro pro;
+};
+__global__ void __launch_bounds__(T3_WARPS * 32)
+    mtf3_starts_kernel(Present present, uint32_t sigma, uint32_t L, uint64_t nchunks, const uint32_t *__restrict__ trow,
+                       const uint32_t *__restrict__ segpre, uint32_t seg_tiles, uint16_t *__restrict__ start,
+                       const uint32_t *__restrict__ finalocc, uint64_t N, uint16_t *__restrict__ final_list) {
+    __shared__ StartsWarp sw[T3_WARPS];
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    if (blockIdx.x == gridDim.x - 1) { // the extra CTA: seqToMTF's second component, the list after the last symbol
+        if (w == 0) final_list_from(finalocc, present, N, sw[0].pro, final_list);
+        return;
+    }
+    const uint64_t tile = (uint64_t)blockIdx.x * T3_WARPS + w;
+    if (tile * 32 >= nchunks) return;
+    StartsWarp &W = sw[w];
+    const unsigned lt = lanemask_lt();
+    // list order at the start of the tile
+    uint32_t lpos[9];
+    {
+        uint32_t tv[9], ord[9];
+        bool valid[9];
+        uint32_t inv_base = sigma;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const uint32_t li = lane + 32 * i;
+            valid[i] = (present.w[i] >> lane) & 1u;
+            ord[i] = li == 256 ? 0u : li + 1u;
+            tv[i] = valid[i] ? max(trow[tile * R3_ROW + li], segpre[(tile / seg_tiles) * R3_ROW + li]) : 0;
+        }
+        list_positions_g(tv, valid, ord, tile * 32 * L, W.pro, lpos);
+#pragma unroll
+        for (int i = 0; i < 9; i++) { // the other entries: positions sigma .. 287, in any fixed order
+            const unsigned b = __ballot_sync(TC_FULL, !valid[i]);
+            if (!valid[i]) lpos[i] = inv_base + __popc(b & lt);
+            inv_base += __popc(b);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j++) (&W.map8[0][0])[lane + 32 * j] = 0;
+    __syncwarp();
+    const uint32_t nt = (uint32_t)(nchunks - tile * 32 < 32 ? nchunks - tile * 32 : 32);
+    uint16_t *row = start + tile * 32 * R3_ROW + lane;
+    // lane-rotated order in which a lane reads the 8 words (32 bytes) of its part of the byte map: no bank conflicts
+    uint32_t woff[8], wsh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        woff[j] = 8 * lane + ((j + lane) & 7u);
+        wsh[j] = 4u * ((j + lane) & 7u);
+    }
+    uint32_t q[9], qn[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) qn[i] = ldg_u16(row + 32 * i);
+    for (uint32_t t = 0; t < nt; t++, row += R3_ROW) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            q[i] = qn[i];
+            row[32 * i] = (uint16_t)(R3_VS - 1 - lpos[i]); // slots of entries behind the sigma codes are never read
+        }
+        if (t + 1 == nt) break;
+#pragma unroll
+        for (int i = 0; i < 9; i++) qn[i] = ldg_u16(row + R3_ROW + 32 * i); // next chunk's q while this one is ranked
+        uint8_t *map = reinterpret_cast<uint8_t *>(W.map8[t & 1]);
+        uint32_t key[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            key[i] = L + lpos[i];          // not seen in the chunk: behind the seen ones, old order kept
+            if (q[i]) key[i] = L - q[i];   // seen: by descending q
+            map[key[i]] = 1;
+        }
+        __syncwarp();
+        {
+            // bytes 32 * lane .. + 31 of the map -> one word of bits
+            const uint32_t *mw = W.map8[t & 1];
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) bits |= ((mw[woff[j]] * 0x01020408u) >> 24) << wsh[j];
+            const uint32_t pc = __popc(bits);
+            W.wp[lane] = make_uint2(bits, warp_incl_sum(pc) - pc);
+            uint32_t *other = W.map8[(t & 1) ^ 1]; // last read before the barrier above
+#pragma unroll
+            for (int j = 0; j < 8; j++) other[lane + 32 * j] = 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const uint2 e = W.wp[key[i] >> 5];
+            lpos[i] = e.y + __popc(e.x & ((1u << (key[i] & 31u)) - 1u));
+        }
+    }
+}
+
+struct R3 {
+    uint16_t *last;  // per-thread base; entry li is li * CT halfwords further on
+    uint32_t *bits;  // per-thread base; consecutive words are CT apart
+    uint64_t *sfx;
+    uint32_t T;      // 3 x 10 bits: live slots in the groups above group g
+    uint32_t ow, e0; // the word being appended to (slots e0 .. e0 + 31), kept in a register
+};
+// Slots e0 .. e0 + 31 are credited to sfx / T as live when their word is opened ("pre-credit"), so a
+// query below the open word reads 32 - (symbols appended so far) too many: the caller subtracts it.
+template <int CT>
+__device__ __forceinline__ void r3_open_word(R3 &S) {
+    const uint32_t we = S.e0 >> 5, ge = we >> 3, ke = we & 7u;
+    S.sfx[ge * CT] += 0x0020202020202020ull >> (56u - 8u * ke);
+    S.T += 0x02008020u >> (30u - 10u * ge);
+    S.ow = 0;
+}
+// One symbol: last-index li, appended as slot e0 + k (bit = 1 << k, corr = 32 - k).  Returns its MTF index
+// = live slots above the slot a of its previous occurrence, and retires a.
+template <int CT>
+__device__ __forceinline__ uint32_t r3_step(R3 &S, const uint64_t *m8tab, uint32_t a, uint32_t bitk, uint32_t corr) {
+    const uint32_t wa = a >> 5, ba = a & 31u, g = a >> 8, kk8 = (a >> 2) & 0x38u, x = 10u * g;
+    const uint32_t w = S.bits[wa * CT];
+    const uint64_t sv = S.sfx[g * CT];
+    const uint64_t m8 = *reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(m8tab) + kk8);
+    const uint32_t bit = 1u << ba;
+    const bool open = a >= S.e0; // in the open word: its bits live in S.ow, the word in memory is still 0
+    const uint32_t closed = __popc(shr_clamp(w, ba + 1u)) + ((uint32_t)(sv >> kk8) & 0xffu) + ((S.T >> x) & 0x3ffu) - corr;
+    const uint32_t inopen = __popc(shr_clamp(S.ow, ba + 1u));
+    S.bits[wa * CT] = w & ~bit;
+    S.sfx[g * CT] = sv - m8;
+    S.T -= 0x00100401u >> (30u - x);
+    S.ow = (S.ow & ~(open ? bit : 0u)) | bitk;
+    return open ? inopen : closed;
+}
+
+template <class Src, int CT>
+__global__ void __launch_bounds__(CT)
+    mtf3_replay_kernel(Src src, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t sigma,
+                       const uint16_t *__restrict__ start, uint16_t *__restrict__ idx_out) {
+    extern __shared__ __align__(16) uint32_t sm3[];
+    __shared__ uint64_t m8tab[8];
+    if (threadIdx.x < 8) m8tab[threadIdx.x] = 0x0001010101010101ull >> (56u - 8u * threadIdx.x); // bytes below kk
+    __syncthreads();
+    const uint64_t k = (uint64_t)blockIdx.x * CT + threadIdx.x;
+    if (k >= nchunks) return;
+    R3 S;
+    S.last = reinterpret_cast<uint16_t *>(sm3) + threadIdx.x;
+    S.bits = sm3 + R3_LASTW * CT + threadIdx.x;
+    S.sfx = reinterpret_cast<uint64_t *>(sm3 + (R3_LASTW + R3_BITW) * CT) + threadIdx.x;
+    // incoming order: the chunk's start row
+    {
+        // 576-byte rows: 8 x 16 bytes in flight per thread
+        const uint4 *row = reinterpret_cast<const uint4 *>(start + k * R3_ROW);
+#pragma unroll 1
+        for (int b = 0; b < 32; b += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = __ldg(row + b + q);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t ws[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int li = 8 * (b + q) + 2 * e;
+                    S.last[li * CT] = (uint16_t)ws[e];
+                    S.last[(li + 1) * CT] = (uint16_t)(ws[e] >> 16);
+                }
+            }
+        }
+        S.last[256 * CT] = start[k * R3_ROW + 256];
+    }
+    // the sigma live slots are R3_VS - sigma .. R3_VS - 1
+    {
+        const int lo = R3_VS - (int)sigma, hi = R3_VS;
+        auto live = [&](int x0, int x1) { // live slots in [x0, x1)
+            int a = x0 > lo ? x0 : lo, b = x1 < hi ? x1 : hi;
+            return b > a ? b - a : 0;
+        };
+#pragma unroll 4
+        for (int w = 0; w < R3_BITW; w++) {
+            int a = 32 * w > lo ? 32 * w : lo, b = 32 * w + 32 < hi ? 32 * w + 32 : hi;
+            uint32_t m = 0;
+            if (b > a) m = (b - a == 32 ? 0xffffffffu : ((1u << (b - a)) - 1u)) << (a - 32 * w);
+            S.bits[w * CT] = m;
+        }
+        S.T = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            uint64_t sv = 0;
+#pragma unroll
+            for (int q = 0; q < 7; q++) sv |= (uint64_t)live(32 * (8 * g + q + 1), 256 * (g + 1)) << (8 * q);
+            S.sfx[g * CT] = sv;
+            if (g < 3) S.T |= (uint32_t)live(256 * (g + 1), 1024) << (10 * g);
+        }
+        S.e0 = R3_VS;
+        r3_open_word<CT>(S);
+    }
+    const uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+    uint64_t pos = beg;
+    const bool vec = src.can_vec(beg) && (reinterpret_cast<uintptr_t>(idx_out + beg) & 15) == 0;
+    // the first word was opened above; every later block files the full word and opens the next one first
+    // (never past the last block: slot 1024 does not exist)
+    bool fresh = true;
+    auto next_word = [&]() {
+        if (!fresh) {
+            S.bits[(S.e0 >> 5) * CT] = S.ow;
+            S.e0 += 32;
+            r3_open_word<CT>(S);
+        }
+        fresh = false;
+    };
+    if (vec) {
+        const uint64_t vend = beg + ((end - beg) & ~31ull); // whole words of 32 symbols
+        typename Src::Raw nxt;
+        if (pos < vend) nxt = src.load_raw(pos);
+        for (; pos < vend; pos += 32) {
+            next_word();
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                uint32_t li[16];
+                const typename Src::Raw now = nxt; // the next 16 symbols are on their way while these are replayed
+                if (pos + 16 * half + 16 < vend) nxt = src.load_raw(pos + 16 * half + 16);
+                src.decode_li(now, pos + 16 * half, li);
+                const uint32_t kb = 16u * half, eb = S.e0 + kb;
+                uint32_t o[8];
+                uint32_t a_next = S.last[li[0] * CT];
+                S.last[li[0] * CT] = (uint16_t)eb;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t a = a_next;
+                    if (j + 1 < 16) { // the next symbol's slot is fetched before this symbol's bitmap traffic
+                        a_next = S.last[li[j + 1] * CT];
+                        S.last[li[j + 1] * CT] = (uint16_t)(eb + j + 1);
+                    }
+                    const uint32_t r = r3_step<CT>(S, m8tab, a, (1u << j) << kb, 32u - j - kb);
+                    o[j >> 1] = (j & 1) ? (o[j >> 1] | (r << 16)) : r;
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(idx_out + pos + 16 * half);
+                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+    // tail of the last chunk, and chunks whose buffers are not 16-byte aligned
+    for (uint32_t j = 0; pos < end; pos++) {
+        if (j == 0) next_word();
+        const uint32_t li = r3_lidx((uint32_t)src.at(pos));
+        const uint32_t a = S.last[li * CT];
+        S.last[li * CT] = (uint16_t)(S.e0 + j);
+        idx_out[pos] = (uint16_t)r3_step<CT>(S, m8tab, a, 1u << j, 32u - j);
+        j = (j + 1) & 31u;
     }
 }
 
@@ -858,13 +1361,14 @@ __global__ void mtfd_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N,
 // (`defer`) the host does not wait here: the RLE stage that follows syncs the stream anyway and
 // mtf_finish_pending() then translates the ranks.  Slot 512.. of h_scal is used by nothing else.
 int mtf_read_final(tc_ctx *ctx, const uint16_t *d_final, uint32_t sigma, const int16_t *alpha, int16_t *final_list,
-                   bool defer) {
+                   bool defer, uint32_t nalpha = 0) { // alpha: device list entry -> symbol (nalpha entries, default sigma)
+    if (!nalpha) nalpha = sigma;
     uint16_t *h_final = (uint16_t *)(ctx->h_scal + 512);
     TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
     if (defer) {
         ctx->mtf_pending.active = true;
         ctx->mtf_pending.sigma = sigma;
-        memcpy(ctx->mtf_pending.alpha, alpha, sigma * sizeof(int16_t));
+        memcpy(ctx->mtf_pending.alpha, alpha, nalpha * sizeof(int16_t));
         ctx->mtf_pending.final_list = final_list;
         return TC_OK;
     }
@@ -928,6 +1432,54 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         return rc;
     }
     const uint32_t VS = (sigma + 31) / 32 * 32;
+    if (!ctx->mtf_v2) { // thread-per-chunk replay (TC_B200_MTF_V2=1 keeps the warp-per-chunk kernel for comparison)
+        // one chunk per resident thread when the input allows it (two CTAs of R3_CT threads per SM)
+        uint64_t Lt = ceil_div_u64(N, (uint64_t)ctx->sm_count * 2 * R3_CT);
+        if (ctx->mtf_L) Lt = ctx->mtf_L;
+        Lt = (Lt + 31) / 32 * 32;
+        const uint32_t L = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(Lt, 128), R3_LMAX);
+        const uint64_t nchunks = ceil_div_u64(N, L), ntiles = ceil_div_u64(nchunks, 32);
+        uint32_t *trow, *finalocc;
+        uint16_t *d_final, *start;
+        TC_TRY(ws_alloc(ctx, ntiles * R3_ROW, &trow));
+        TC_TRY(ws_alloc(ctx, R3_ROW + 32, &finalocc)); // + the ticket of the scan kernel's last-CTA election
+        uint32_t *segpre;
+        TC_TRY(ws_alloc(ctx, (size_t)T2_SEGS * R3_ROW, &segpre));
+        const uint32_t seg_tiles = (uint32_t)std::max<uint64_t>(1, ceil_div_u64(ntiles, T2_SEGS));
+        TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+        TC_TRY(ws_alloc(ctx, nchunks * R3_ROW, &start));
+        uint32_t *ticket = finalocc + R3_ROW;
+        Present pr;
+        memset(&pr, 0, sizeof pr);
+        int16_t alpha_li[SIGMAX]; // li -> symbol
+        for (int c = 0; c < SIGMAX; c++) {
+            const int li = c == 0 ? 256 : c - 1;
+            alpha_li[li] = (int16_t)(c - 1);
+            if (h_present[c]) pr.w[li >> 5] |= 1u << (li & 31);
+        }
+        const size_t smem1 = (size_t)T1_WARPS * 32 * TP_RLW * sizeof(uint32_t);
+        const size_t smem3 = (size_t)R3_WORDS * R3_CT * sizeof(uint32_t);
+        const uint32_t abit = sizeof(*src.p) == 1 ? 1u : 2u;
+        if (!(ctx->attr_done & abit)) {
+            TC_CUDA(cudaFuncSetAttribute(mtf3_tile_last_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            TC_CUDA(cudaFuncSetAttribute(mtf3_replay_kernel<Src, R3_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem3));
+            ctx->attr_done |= abit;
+        }
+        TC_LAUNCH(ctx, (mtf3_tile_last_kernel<Src>), (unsigned)ceil_div_u64(ntiles, T1_WARPS), T1_WARPS * 32, smem1, src, N,
+                  L, nchunks, trow, start, ticket);
+        TC_LAUNCH(ctx, mtf3_tile_scan_kernel, dim3(R3_ROW / 32, T2_SEGS), T2_WARPS * 32, 0, trow, ntiles, seg_tiles, segpre,
+                  finalocc, ticket);
+        TC_LAUNCH(ctx, mtf3_starts_kernel, (unsigned)ceil_div_u64(ntiles, T3_WARPS) + 1, T3_WARPS * 32, 0, pr, sigma, L,
+                  nchunks, trow, segpre, seg_tiles, start, finalocc, N, d_final);
+        ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
+        TC_LAUNCH(ctx, (mtf3_replay_kernel<Src, R3_CT>), (unsigned)ceil_div_u64(nchunks, R3_CT), R3_CT, smem3, src, N, L,
+                  nchunks, sigma, start, d_idx);
+        *sigma_out = sigma;
+        int rc = mtf_read_final(ctx, d_final, sigma, alpha_li, final_list, present_hint != nullptr, SIGMAX);
+        tc_ws_release(ctx, mk);
+        return rc;
+    }
     // chunk length: a multiple of 32, enough chunks to fill the machine with warps
     uint64_t Lw = ceil_div_u64(N, (uint64_t)ctx->sm_count * 64);
     Lw = (Lw + 31) / 32 * 32;
