@@ -50,6 +50,7 @@ struct tc_ctx {
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     bool mtf_v2 = false; // TC_B200_MTF_V2=1: warp-per-chunk MTF replay (the round-1 kernel) instead of thread-per-chunk
     uint32_t mtf_L = 0;  // TC_B200_MTF_L: chunk length of the thread-per-chunk MTF replay (0 = one chunk per resident thread)
+    void *mtf_auto[9] = {nullptr}; // per alphabet size: device tables of the MTF automata (mtf.cu: AutoTables)
     uint32_t attr_done = 0; // kernels whose dynamic shared-memory limit has been raised on this context's device
     char err[512] = {0};
     // optional per-kernel timing (tc_ctx_profile): one event pair per launch

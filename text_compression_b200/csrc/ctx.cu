@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "impl.cuh"
 
 static const size_t kAlign = 512;
 
@@ -82,6 +83,7 @@ extern "C" void tc_ctx_destroy(tc_ctx *ctx) {
     for (tc_ctx *c : ctx->child) tc_ctx_destroy(c);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    mtf_free_tables(ctx);
     for (auto &c : ctx->chunks) cudaFree(c.p);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);

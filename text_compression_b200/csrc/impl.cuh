@@ -13,6 +13,7 @@ int bwt_decode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_bwt, uint64_t N, uint8
 int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
                            int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint = nullptr);
 int mtf_finish_pending(tc_ctx *ctx); // see mtf.cu: deferred final list of the composed helpers
+void mtf_free_tables(tc_ctx *ctx);   // device tables of the small-alphabet automata
 int mtf_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint16_t *d_idx, int16_t *final_list,
                             uint32_t *sigma);
 int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const int16_t *final_list, uint32_t sigma_in,

@@ -1105,6 +1105,215 @@ __global__ void __launch_bounds__(SM_T)
     }
 }
 
+// ---- encode, sigma <= 6 (ACGT / ACGTN + sentinel): a permutation automaton in shared memory --------------
+// With at most 6 symbols the whole MTF list is one of 720 permutations, so a symbol costs one table lookup
+// instead of the ~30 register instructions of the nibble list above:
+//   entry[state][column] = (5 * next state) << 3 | MTF index,  state = Lehmer rank of the list
+// Rows are 5 words apart (4 words of entries + 1 of padding) so that the 32 lanes' states fall into all 32 banks
+// (16-byte rows use 8 classes of 4 banks: measured ~7 wavefronts per lookup), and the column of a symbol is a
+// multiplicative hash of its byte found on the host to be injective on the alphabet -- no rank table lookup:
+// the kernels are bound by shared-memory instruction issue (~8 cycles per LDS measured), not by arithmetic.
+// The summary pass runs the same automaton from the identity and collects the set of columns seen: the
+// chunk's recency list is the front of the list it ends with.  The table is rebuilt on the host when the
+// alphabet changes (720 x 8 entries).
+// Threads own chunks of AU_L consecutive symbols, so a warp's loads and stores would touch 32 different
+// 128-byte lines per instruction (2 cycles each in L1TEX: measured 22 us of a 35 us kernel).  Instead the warp
+// copies its 32 chunks (4 KB contiguous) through padded shared-memory rows: whole lines in, whole lines out.
+constexpr int AU_L = 128; // symbols per thread
+constexpr int AU_T = 256; // threads per CTA
+constexpr int AU_MAXSIG = 6;
+constexpr int AU_ROW = AU_L + 16; // bytes per staged row: consecutive lanes' 16-byte pieces fall into different banks
+
+__host__ __device__ inline uint32_t perm_rank(uint32_t list, uint32_t sigma) { // Lehmer rank of the nibble list
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < sigma; i++) {
+        const uint32_t a = (list >> (4 * i)) & 15u;
+        uint32_t c = 0;
+        for (uint32_t j = i + 1; j < sigma; j++) c += ((list >> (4 * j)) & 15u) < a;
+        r = r * (sigma - i) + c;
+    }
+    return r;
+}
+
+struct AutoHash { // column of a symbol: ((li * mul) >> shift) & 14 is twice its column
+    uint32_t mul, shift;
+    __host__ __device__ uint32_t col2(uint32_t li) const { return ((li * mul) >> shift) & 14u; }
+};
+constexpr int AU_RW = 10; // u16 entries per table row (8 + padding): odd number of words
+struct AutoSmem { // the dynamic shared memory of both kernels
+    uint16_t perm[720 * AU_RW];
+    uint32_t list[720];               // state -> nibble list
+    uint8_t rows[AU_T / 32][32 * AU_ROW];
+};
+__device__ __forceinline__ void auto_load_tables(AutoSmem &A, const uint16_t *__restrict__ g_perm,
+                                                 const uint32_t *__restrict__ g_list, uint32_t n_perm) {
+    // rows of 5 words, word-wise: n_perm * 5 words of table + n_perm lists, all loads of a thread in flight
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(g_perm);
+    uint32_t *d = reinterpret_cast<uint32_t *>(A.perm);
+    const uint32_t nw = n_perm * (AU_RW / 2);
+    uint32_t tr[15], tl[3];
+#pragma unroll
+    for (int q = 0; q < 15; q++)
+        if (threadIdx.x + AU_T * q < nw) tr[q] = __ldg(g + threadIdx.x + AU_T * q);
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+        if (threadIdx.x + AU_T * q < n_perm) tl[q] = __ldg(g_list + threadIdx.x + AU_T * q);
+#pragma unroll
+    for (int q = 0; q < 15; q++)
+        if (threadIdx.x + AU_T * q < nw) d[threadIdx.x + AU_T * q] = tr[q];
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+        if (threadIdx.x + AU_T * q < n_perm) A.list[threadIdx.x + AU_T * q] = tl[q];
+}
+// the warp's 32 chunks (32 * AU_L contiguous bytes at g) -> rows; lane l then owns row l
+__device__ __forceinline__ void auto_stage_in(const uint8_t *__restrict__ g, uint8_t *rows) {
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int i = 0; i < AU_L / 16; i++) {
+        const uint32_t off = (i * 32 + lane) * 16;
+        *reinterpret_cast<uint4 *>(rows + (off / AU_L) * AU_ROW + (off % AU_L)) = ld_stream_u4(g + off);
+    }
+    __syncwarp();
+}
+
+template <class Src>
+__global__ void __launch_bounds__(AU_T, 4)
+    mtfa_summary_kernel(Src src, AutoHash hs, uint64_t N, const uint16_t *__restrict__ g_perm,
+                        const uint32_t *__restrict__ g_list, uint32_t n_perm, Summ *__restrict__ part,
+                        Summ *__restrict__ tot) {
+    extern __shared__ __align__(16) uint32_t sma[];
+    AutoSmem &A = *reinterpret_cast<AutoSmem *>(sma);
+    __shared__ Summ wsum[AU_T / 32];
+    auto_load_tables(A, g_perm, g_list, n_perm);
+    __syncthreads();
+    const uint64_t chunk = (uint64_t)blockIdx.x * AU_T + threadIdx.x;
+    const uint64_t base = chunk * AU_L;
+    const uint64_t wbase = (chunk & ~31ull) * AU_L; // first symbol of the warp's 32 chunks
+    const char *tab = reinterpret_cast<const char *>(A.perm);
+    uint32_t st = 0, mask = 0; // the identity is permutation 0
+    bool done = false;
+    if constexpr (sizeof(*src.p) == 1) {
+        if (wbase + 32 * AU_L <= N && src.can_vec(wbase)) { // warp-uniform
+            uint8_t *rows = A.rows[threadIdx.x >> 5];
+            auto_stage_in(reinterpret_cast<const uint8_t *>(src.p) + wbase, rows);
+            const uint4 *mine = reinterpret_cast<const uint4 *>(rows + lane_id() * AU_ROW);
+#pragma unroll
+            for (int q = 0; q < AU_L / 16; q++) {
+                uint32_t li[16], r[16];
+                src.decode_li(typename Src::Raw{mine[q]}, base + 16 * q, li);
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    r[k] = hs.col2(li[k]);
+                    mask |= 1u << r[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++) st = (*reinterpret_cast<const uint16_t *>(tab + st + r[k]) & 0xfff8u) >> 1;
+            }
+            done = true;
+        }
+    }
+    if (!done && base < N) {
+        const uint64_t end = base + AU_L < N ? base + AU_L : N;
+        for (uint64_t pos = base; pos < end; pos++) {
+            const uint32_t r = hs.col2(r3_lidx((uint32_t)src.at(pos)));
+            mask |= 1u << r;
+            st = (*reinterpret_cast<const uint16_t *>(tab + st + r) & 0xfff8u) >> 1;
+        }
+    }
+    // the chunk's recency list = the first popc(mask) entries of the list it leaves behind (mask: columns seen)
+    Summ v{0, 0};
+    {
+        const uint32_t k = (uint32_t)__popc(mask);
+        const uint32_t l = A.list[st / (2 * AU_RW)];
+        v.list = k >= 8 ? l : (l & ((1u << (4 * k)) - 1u));
+        for (uint32_t j = 0; j < k; j++) v.mask |= 1u << ((l >> (4 * j)) & 15u);
+    }
+    // inclusive scan over the warp, then over the CTA's warps
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Summ o = summ_shfl_up(v, d);
+        if (lane >= (unsigned)d) v = summ_compose(o, v);
+    }
+    const int w = threadIdx.x >> 5;
+    if (lane == 31) wsum[w] = v;
+    Summ ex = summ_shfl_up(v, 1);
+    if (lane == 0) ex = Summ{0, 0};
+    __syncthreads();
+    Summ pre{0, 0};
+    for (int ww = 0; ww < w; ww++) pre = summ_compose(pre, wsum[ww]);
+    if (base < N) part[chunk] = summ_compose(pre, ex);
+    if (threadIdx.x == AU_T - 1) tot[blockIdx.x] = summ_compose(pre, v);
+}
+
+template <class Src>
+__global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 16 MiB block are one wave
+    mtfa_replay_kernel(Src src, AutoHash hs, uint64_t N, const uint16_t *__restrict__ g_perm,
+                       const uint32_t *__restrict__ g_list, uint32_t n_perm, const Summ *__restrict__ part,
+                       const uint32_t *__restrict__ start_list, uint32_t sigma, uint16_t *__restrict__ idx_out) {
+    extern __shared__ __align__(16) uint32_t sma[];
+    AutoSmem &A = *reinterpret_cast<AutoSmem *>(sma);
+    auto_load_tables(A, g_perm, g_list, n_perm);
+    __syncthreads();
+    const uint64_t chunk = (uint64_t)blockIdx.x * AU_T + threadIdx.x;
+    const uint64_t base = chunk * AU_L;
+    const uint64_t wbase = (chunk & ~31ull) * AU_L;
+    if (wbase >= N) return;
+    const char *tab = reinterpret_cast<const char *>(A.perm);
+    const uint32_t full = (1u << sigma) - 1u;
+    uint32_t st = 0;
+    if (base < N) st = perm_rank(summ_compose(Summ{start_list[blockIdx.x], full}, part[chunk]).list, sigma) * (2 * AU_RW);
+    if constexpr (sizeof(*src.p) == 1) {
+        if (wbase + 32 * AU_L <= N && src.can_vec(wbase) && (reinterpret_cast<uintptr_t>(idx_out + wbase) & 15) == 0) {
+            const unsigned lane = lane_id();
+            uint8_t *rows = A.rows[threadIdx.x >> 5];
+            auto_stage_in(reinterpret_cast<const uint8_t *>(src.p) + wbase, rows);
+            uint4 raw[AU_L / 16];
+#pragma unroll
+            for (int q = 0; q < AU_L / 16; q++) raw[q] = reinterpret_cast<const uint4 *>(rows + lane * AU_ROW)[q];
+            __syncwarp(); // the rows are free: they take the indices, 64 symbols (128 bytes) per lane at a time
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int q = 0; q < AU_L / 32; q++) {
+                    uint32_t li[16], r[16], o[8];
+                    src.decode_li(typename Src::Raw{raw[h * (AU_L / 32) + q]}, base + 16 * (h * (AU_L / 32) + q), li);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) r[k] = hs.col2(li[k]);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const uint32_t e = *reinterpret_cast<const uint16_t *>(tab + st + r[k]);
+                        const uint32_t x = e & 7u;
+                        st = (e & 0xfff8u) >> 1;
+                        o[k >> 1] = (k & 1) ? (o[k >> 1] | (x << 16)) : x;
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(rows + lane * AU_ROW + 32 * q);
+                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                __syncwarp();
+                // 32 rows x 128 bytes of indices -> the 64 symbols at offset 64 h of every chunk (128 B at stride 256 B)
+                uint8_t *gout = reinterpret_cast<uint8_t *>(idx_out + wbase) + 2 * (AU_L / 2) * h;
+#pragma unroll
+                for (int i = 0; i < AU_L / 16; i++) {
+                    const uint32_t off = (i * 32 + lane) * 16; // byte offset in the 32 x 128-byte block
+                    const uint32_t row = off / AU_L, within = off % AU_L;
+                    st_stream_u4(gout + (size_t)row * (2 * AU_L) + within, *reinterpret_cast<const uint4 *>(rows + row * AU_ROW + within));
+                }
+                __syncwarp();
+            }
+            return;
+        }
+    }
+    if (base >= N) return;
+    const uint64_t end = base + AU_L < N ? base + AU_L : N;
+    for (uint64_t pos = base; pos < end; pos++) {
+        const uint32_t e = *reinterpret_cast<const uint16_t *>(tab + st + hs.col2(r3_lidx((uint32_t)src.at(pos))));
+        idx_out[pos] = (uint16_t)(e & 7u);
+        st = (e & 0xfff8u) >> 1;
+    }
+}
+
 // ---- decode ----------------------------------------------------------------------------------
 // D1: permutation each chunk applies to list positions (replay on the identity list).
 __global__ void mtfd_perm_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t L, uint64_t nchunks,
@@ -1377,6 +1586,87 @@ int mtf_read_final(tc_ctx *ctx, const uint16_t *d_final, uint32_t sigma, const i
     return TC_OK;
 }
 
+// Host side of the automaton: rebuilt when the alphabet changes, kept in device memory.
+struct AutoTables {
+    uint32_t n_perm = 0;
+    uint16_t *d_perm = nullptr;
+    uint32_t *d_list = nullptr;
+    AutoHash hash{0, 0};
+    uint32_t sigma = 0;
+    uint16_t li_of_rank[8] = {0};
+};
+// li_of_rank[r], r < sigma: the symbols of the alphabet in order (Nothing = 256 first if present)
+int auto_tables(tc_ctx *ctx, uint32_t sigma, const uint16_t *li_of_rank, AutoTables *out) {
+    AutoTables *t = static_cast<AutoTables *>(ctx->mtf_auto[0]);
+    if (t && t->sigma == sigma && memcmp(t->li_of_rank, li_of_rank, sigma * sizeof(uint16_t)) == 0) {
+        *out = *t;
+        return TC_OK;
+    }
+    // column hash: an odd multiplier and a shift that send the alphabet to distinct columns 0..7
+    AutoHash hs{0, 0};
+    uint32_t colof[8];
+    {
+        uint64_t x = 0x9E3779B97F4A7C15ull;
+        bool ok = false;
+        for (int tries = 0; tries < 200000 && !ok; tries++) {
+            x ^= x << 13, x ^= x >> 7, x ^= x << 17; // xorshift64
+            hs.mul = (uint32_t)(x >> 16) | 1u;
+            for (uint32_t sh = 0; sh < 29 && !ok; sh++) {
+                hs.shift = sh;
+                uint32_t used = 0;
+                ok = true;
+                for (uint32_t r = 0; r < sigma && ok; r++) {
+                    colof[r] = hs.col2(li_of_rank[r]) >> 1;
+                    ok = !((used >> colof[r]) & 1u);
+                    used |= 1u << colof[r];
+                }
+            }
+        }
+        if (!ok) return TC_E_ARG; // cannot happen for <= 6 symbols and 8 columns
+    }
+    uint32_t nperm = 1;
+    for (uint32_t i = 2; i <= sigma; i++) nperm *= i;
+    std::vector<uint16_t> perm((size_t)nperm * AU_RW, 0);
+    std::vector<uint32_t> lists(nperm);
+    {
+        uint32_t p[8];
+        for (uint32_t i = 0; i < sigma; i++) p[i] = i;
+        do {
+            uint32_t l = 0;
+            for (uint32_t i = 0; i < sigma; i++) l |= p[i] << (4 * i);
+            lists[perm_rank(l, sigma)] = l;
+        } while (std::next_permutation(p, p + sigma));
+    }
+    for (uint32_t id = 0; id < nperm; id++) {
+        const uint32_t l = lists[id];
+        for (uint32_t c = 0; c < 8; c++) perm[(size_t)id * AU_RW + c] = (uint16_t)((5 * id) << 3); // no-op
+        for (uint32_t sy = 0; sy < sigma; sy++) {
+            uint32_t pos = 0;
+            while (((l >> (4 * pos)) & 15u) != sy) pos++;
+            const uint32_t low = (1u << (4 * pos)) - 1u;
+            const uint32_t nl = (l & ~((low << 4) | 0xFu)) | ((l & low) << 4) | sy;
+            perm[(size_t)id * AU_RW + colof[sy]] = (uint16_t)(((5 * perm_rank(nl, sigma)) << 3) | pos);
+        }
+    }
+    if (!t) {
+        t = new AutoTables();
+        TC_CUDA(cudaMalloc((void **)&t->d_perm, 720 * AU_RW * sizeof(uint16_t)));
+        TC_CUDA(cudaMalloc((void **)&t->d_list, 720 * sizeof(uint32_t)));
+        ctx->mtf_auto[0] = t;
+    }
+    t->sigma = 0; // invalid until the upload below has succeeded
+    TC_CUDA(cudaStreamSynchronize(ctx->stream)); // an earlier block may still be reading the old table
+    TC_CUDA(cudaMemcpyAsync(t->d_perm, perm.data(), perm.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    TC_CUDA(cudaMemcpyAsync(t->d_list, lists.data(), lists.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    TC_CUDA(cudaStreamSynchronize(ctx->stream)); // the vectors go away
+    t->n_perm = nperm;
+    t->hash = hs;
+    t->sigma = sigma;
+    memcpy(t->li_of_rank, li_of_rank, sigma * sizeof(uint16_t));
+    *out = *t;
+    return TC_OK;
+}
+
 // present_hint (257 flags, code = symbol + 1, 0 = Nothing): the alphabet when the caller already
 // knows it (the composed helpers do: a BWT has the symbols of its text plus the sentinel)
 template <class Src>
@@ -1411,6 +1701,38 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         } else {
             lut.rank[c] = 0;
         }
+    }
+    if (sigma <= AU_MAXSIG && !ctx->mtf_v2) { // automata in shared memory
+        AutoTables at;
+        uint16_t li_of_rank[8];
+        for (uint32_t j = 0; j < sigma; j++) li_of_rank[j] = (uint16_t)(alpha[j] < 0 ? 256 : alpha[j]);
+        TC_TRY(auto_tables(ctx, sigma, li_of_rank, &at));
+        const uint64_t nchunks = ceil_div_u64(N, AU_L), ntiles = ceil_div_u64(nchunks, AU_T);
+        Summ *part, *tot;
+        uint32_t *start_list;
+        uint16_t *d_final;
+        TC_TRY(ws_alloc(ctx, ntiles * AU_T, &part));
+        TC_TRY(ws_alloc(ctx, ntiles, &tot));
+        TC_TRY(ws_alloc(ctx, ntiles, &start_list));
+        TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+        const size_t sma = sizeof(AutoSmem);
+        const uint32_t abit = sizeof(*src.p) == 1 ? 4u : 8u;
+        if (!(ctx->attr_done & abit)) {
+            TC_CUDA(cudaFuncSetAttribute(mtfa_summary_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+            TC_CUDA(cudaFuncSetAttribute(mtfa_replay_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+            ctx->attr_done |= abit;
+        }
+        ctx->prof_bytes_next = N * sizeof(*src.p);
+        TC_LAUNCH(ctx, (mtfa_summary_kernel<Src>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list, at.n_perm,
+                  part, tot);
+        TC_LAUNCH(ctx, mtfs_top_kernel, 1, 1024, 0, tot, ntiles, sigma, start_list, d_final);
+        ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
+        TC_LAUNCH(ctx, (mtfa_replay_kernel<Src>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list, at.n_perm,
+                  part, start_list, sigma, d_idx);
+        *sigma_out = sigma;
+        int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
+        tc_ws_release(ctx, mk);
+        return rc;
     }
     if (sigma <= 8) { // the list fits one register
         const uint64_t nchunks = ceil_div_u64(N, SM_L), ntiles = ceil_div_u64(nchunks, SM_T);
@@ -1507,6 +1829,17 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
     return rc;
 }
 } // namespace
+
+void mtf_free_tables(tc_ctx *ctx) {
+    for (void *&p : ctx->mtf_auto) {
+        if (!p) continue;
+        AutoTables *t = static_cast<AutoTables *>(p);
+        cudaFree(t->d_perm);
+        cudaFree(t->d_list);
+        delete t;
+        p = nullptr;
+    }
+}
 
 // after a stream sync: the deferred final list of the last mtf_encode with an alphabet hint
 int mtf_finish_pending(tc_ctx *ctx) {

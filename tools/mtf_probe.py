@@ -17,6 +17,7 @@ kernels = sys.argv[3] if len(sys.argv) > 3 else "01"   # "0": thread-per-chunk, 
 rng = np.random.default_rng(5)
 streams = {
     "bytes": gen_bytes(0xC2, n),
+    "acgtn": gen_acgtn(0xC5, n),
     "ascii": gen_ascii(0xC2B, n),
     "skew96": (32 + np.minimum(rng.geometric(0.35, size=n) - 1, 94)).astype(np.uint8),
 }
