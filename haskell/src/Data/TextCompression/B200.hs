@@ -11,7 +11,9 @@
 -- export lists stay as they are (see INTEGRATION.md for the per-function patch).
 --
 -- NOTE: written without a Haskell toolchain (no GHC in the build image or on the GPU box);
--- it targets base ^>=4.12 / containers 0.6 like the reference, but has not been compiled.
+-- it targets base ^>=4.12 / containers 0.6 like the reference, but HAS NOT BEEN COMPILED.  What can be checked
+-- without GHC is checked: tests/c/abi_layout.c restates every foreign import below as a C prototype against
+-- include/tc_b200.h and pins the struct offsets used here (544 / 552 / 16) with offsetof / sizeof.
 -- All semantics live below the C ABI, where they are tested bit-for-bit against the CPU
 -- restatement of the reference (tests/test_gpu_parity.py).
 --
@@ -22,6 +24,7 @@
 module Data.TextCompression.B200
   ( -- * context
     withB200
+  , deviceCount
     -- * Data.BWT.Internal replacements
   , createSuffixArrayW8
   , toBWTW8
@@ -43,6 +46,12 @@ module Data.TextCompression.B200
   , buildFMIndexW8
   , countFMIndexW8
   , locateFMIndexW8
+    -- * the same over every GPU of the box (one library call; mirrors parListChunk over the cores)
+  , compressBlocksPackedMultiW8
+  , B200FMs
+  , replicateFMIndexW8
+  , countFMIndexMultiW8
+  , locateFMIndexMultiW8
   ) where
 
 import           Control.Exception     (ErrorCall (..), bracket, throwIO)
@@ -62,14 +71,26 @@ import           Foreign.Marshal.Array (peekArray, pokeArray, withArray)
 import           Foreign.Marshal.Utils (withMany)
 import           Foreign.Ptr           (FunPtr, Ptr, castPtr, nullPtr)
 import           Foreign.Storable      (peek, peekByteOff)
+import           System.Environment   (lookupEnv)
 import           System.IO.Unsafe      (unsafePerformIO)
 
 data TcCtx
 data TcFm
 
 -- include/tc_b200.h ------------------------------------------------------------------
-foreign import ccall safe "tc_ctx_create"   c_ctx_create  :: CInt -> Ptr (Ptr TcCtx) -> IO CInt
-foreign import ccall safe "tc_ctx_destroy"  c_ctx_destroy :: Ptr TcCtx -> IO ()
+foreign import ccall safe "tc_ctx_pool_acquire" c_pool_acquire :: CInt -> Ptr (Ptr TcCtx) -> IO CInt
+foreign import ccall safe "tc_ctx_pool_release" c_pool_release :: Ptr TcCtx -> IO ()
+foreign import ccall unsafe "tc_device_count"   c_device_count :: IO CInt
+foreign import ccall safe "tc_mgpu_blocks_encode_packed"
+  c_mgpu_blocks_encode_packed :: CInt -> Ptr CInt -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> CInt -> Ptr (Ptr Word8)
+                              -> Ptr Word64 -> Ptr Word64 -> Ptr () -> IO CInt
+foreign import ccall safe "tc_fm_replicate"
+  c_fm_replicate :: Ptr TcFm -> CInt -> Ptr CInt -> Ptr (Ptr TcFm) -> IO CInt
+foreign import ccall safe "tc_mgpu_fm_count"
+  c_mgpu_fm_count :: CInt -> Ptr CInt -> Ptr (Ptr TcFm) -> Ptr Word8 -> Ptr Word64 -> Word64 -> Ptr Int64 -> IO CInt
+foreign import ccall safe "tc_mgpu_fm_locate"
+  c_mgpu_fm_locate :: CInt -> Ptr CInt -> Ptr (Ptr TcFm) -> Ptr Word8 -> Ptr Word64 -> Word64 -> Ptr Word64
+                   -> Ptr Word64 -> Word64 -> Ptr Word64 -> IO CInt
 foreign import ccall safe "tc_strerror"     c_strerror    :: CInt -> IO CString
 foreign import ccall safe "tc_last_error"   c_last_error  :: Ptr TcCtx -> IO CString
 foreign import ccall safe "tc_host_alloc"   c_host_alloc  :: CSize -> IO (Ptr a)
@@ -117,15 +138,29 @@ tcECap      = -2
 tcEFromJust = -3
 tcEIndex    = -4
 
--- | One context per call keeps the functions pure and re-entrant, like the reference's
--- (`tc_ctx` must not be shared between OS threads).  A long-running caller can hoist this.
+-- | The process-wide context of the device (tc_ctx_pool_acquire: created on first use, exclusive while the
+-- action runs, never destroyed), so a pure call costs no stream / arena / pinned-page set-up.  The device is
+-- TC_B200_DEVICE (default 0).  Calls from several Haskell threads serialise on the device's context; the
+-- ...Multi functions below use one context per GPU.
 withB200 :: (Ptr TcCtx -> IO a) -> IO a
-withB200 = bracket create c_ctx_destroy
+withB200 = bracket acquire c_pool_release
   where
-    create = alloca $ \pp -> do
-      rc <- c_ctx_create 0 pp
+    acquire = alloca $ \pp -> do
+      dev <- maybe 0 read <$> lookupEnv "TC_B200_DEVICE"
+      rc  <- c_pool_acquire dev pp
       when (rc /= 0) $ c_strerror rc >>= peekCString >>= throwIO . ErrorCall
       peek pp
+
+-- | GPUs visible to the process (0: none, and every compute call throws -- there is no CPU path).
+deviceCount :: Int
+deviceCount = fromIntegral (unsafePerformIO c_device_count)
+
+checkRc :: CInt -> IO ()
+checkRc rc
+  | rc == 0           = pure ()
+  | rc == tcEFromJust = throwIO (ErrorCall "Maybe.fromJust: Nothing")
+  | rc == tcEIndex    = throwIO (ErrorCall "index out of bounds")
+  | otherwise         = c_strerror rc >>= peekCString >>= throwIO . ErrorCall . ("libtc_b200: " ++)
 
 check :: Ptr TcCtx -> CInt -> IO ()
 check ctx rc
@@ -376,5 +411,75 @@ locateFMIndexW8 (B200FM fm) pats = unsafePerformIO $ withB200 $ \ctx -> withFore
         c_fm_locate ctx pfm (castPtr pp) po (fromIntegral q) ph ppos (fromIntegral total) pt >>= check ctx
         hs <- map fromIntegral <$> (peekArray (q + 1) ph :: IO [Word64])
         ps <- map fromIntegral <$> (peekArray total ppos :: IO [Word64])
-        forM (zip hs (tail hs)) $ \(a, b) ->
-          pure (DS.fromList (map Just (take (b - a) (drop a ps))))
+        pure (slices hs (DS.fromList (map Just ps)))
+
+-- | Consecutive slices @[o0, o1), [o1, o2), ...@ of a sequence: O(log) per slice, not O(total).
+slices :: [Int] -> Seq a -> [Seq a]
+slices offs s = zipWith (\a b -> DS.take (b - a) (DS.drop a s)) offs (drop 1 offs)
+
+-- | 'compressBlocksPackedW8' over all GPUs of the box: block b runs on device b `mod` (number of devices).
+compressBlocksPackedMultiW8 :: [BS.ByteString] -> [BS.ByteString]
+compressBlocksPackedMultiW8 []     = []
+compressBlocksPackedMultiW8 blocks = unsafePerformIO $ do
+  let nb   = length blocks
+      ns   = map (fromIntegral . BS.length) blocks :: [Word64]
+      devs = [0 .. fromIntegral (max 1 deviceCount) - 1] :: [CInt]
+  caps <- mapM c_packed_bound ns
+  outs <- mapM (pinned . fromIntegral) caps :: IO [ForeignPtr Word8]
+  info <- pinned (552 * nb)
+  withMany BSU.unsafeUseAsCStringLen blocks $ \ins ->
+    withMany withForeignPtr outs $ \pouts ->
+      withArray (map (castPtr . fst) ins) $ \ptext -> withArray devs $ \pdev ->
+        withArray ns $ \pn -> withArray pouts $ \pout -> withArray caps $ \pcap ->
+          withArray (replicate nb 0) $ \pbytes -> withForeignPtr info $ \pinfo -> do
+            c_mgpu_blocks_encode_packed (fromIntegral (length devs)) pdev (fromIntegral nb) ptext pn 1 pout pcap pbytes pinfo
+              >>= checkRc
+            sizes <- peekArray nb pbytes
+            forM (zip pouts sizes) $ \(po, sz) -> BS.packCStringLen (castPtr po, fromIntegral sz)
+
+-- | One replica of an index per GPU (tc_fm_replicate: peer copies of the image over NVLink).
+data B200FMs = B200FMs [CInt] [ForeignPtr TcFm]
+
+replicateFMIndexW8 :: B200FM -> B200FMs
+replicateFMIndexW8 (B200FM root) = unsafePerformIO $ withForeignPtr root $ \proot -> do
+  let devs = [0 .. fromIntegral (max 1 deviceCount) - 1] :: [CInt]
+      nd   = length devs
+  withArray devs $ \pdev -> withArray (replicate nd nullPtr) $ \prep -> do
+    c_fm_replicate proot (fromIntegral nd) pdev prep >>= checkRc
+    reps <- peekArray nd prep
+    B200FMs devs <$> mapM (newForeignPtr p_fm_free) reps
+
+-- | 'countFMIndexW8' with the patterns split into contiguous chunks, one per GPU; input order is kept.
+countFMIndexMultiW8 :: B200FMs -> [BS.ByteString] -> [Maybe Int]
+countFMIndexMultiW8 (B200FMs devs reps) pats = unsafePerformIO $ do
+  let (flat, offs) = packPatterns pats
+      q = length pats
+  off <- pinned (8 * (q + 1))
+  out <- pinned (8 * max 1 q)
+  withMany withForeignPtr reps $ \preps -> withArray preps $ \prep -> withArray devs $ \pdev ->
+    BSU.unsafeUseAsCStringLen flat $ \(pp, _) -> withForeignPtr off $ \po -> withForeignPtr out $ \pc -> do
+      pokeArray po offs
+      c_mgpu_fm_count (fromIntegral (length devs)) pdev prep (castPtr pp) po (fromIntegral q) pc >>= checkRc
+      map (\c -> if c < 0 then Nothing else Just (fromIntegral c)) <$> (peekArray q pc :: IO [Int64])
+
+-- | 'locateFMIndexW8' over all GPUs.
+locateFMIndexMultiW8 :: B200FMs -> [BS.ByteString] -> [Seq (Maybe Int)]
+locateFMIndexMultiW8 (B200FMs devs reps) pats = unsafePerformIO $ do
+  let (flat, offs) = packPatterns pats
+      q  = length pats
+      nd = fromIntegral (length devs)
+  off  <- pinned (8 * (q + 1))
+  hoff <- pinned (8 * (q + 1))
+  withMany withForeignPtr reps $ \preps -> withArray preps $ \prep -> withArray devs $ \pdev ->
+    BSU.unsafeUseAsCStringLen flat $ \(pp, _) -> withForeignPtr off $ \po -> withForeignPtr hoff $ \ph ->
+      alloca $ \pt -> do
+        pokeArray po offs
+        rc <- c_mgpu_fm_locate nd pdev prep (castPtr pp) po (fromIntegral q) ph nullPtr 0 pt   -- sizing call
+        when (rc /= 0 && rc /= tcECap) $ checkRc rc
+        total <- fromIntegral <$> peek pt
+        pos <- pinned (8 * max 1 total)
+        withForeignPtr pos $ \ppos -> do
+          c_mgpu_fm_locate nd pdev prep (castPtr pp) po (fromIntegral q) ph ppos (fromIntegral total) pt >>= checkRc
+          hs <- map fromIntegral <$> (peekArray (q + 1) ph :: IO [Word64])
+          ps <- map fromIntegral <$> (peekArray total ppos :: IO [Word64])
+          pure (slices hs (DS.fromList (map Just ps)))

@@ -22,7 +22,9 @@
  *     H2D/D2H copies themselves; `_dev` entry points take DEVICE pointers on the
  *     context's device and enqueue on the context's stream.
  *   - one tc_ctx per calling OS thread; distinct contexts are fully concurrent.
- *   - sizes: n < 2^32 - 2 (TC_E_TOOBIG otherwise).
+ *   - sizes: n < 2^32 - 2 for the BWT / RLE / FM-index entry points, and N = n + 1 < 2^31 - 1 wherever MTF
+ *     takes part (tc_mtf_encode*, tc_bwt_mtf_rle_encode*, tc_blocks_encode* with with_mtf != 0): recency
+ *     keys are 32-bit distances.  TC_E_TOOBIG otherwise, checked before any work is queued.
  *   - there is NO CPU fallback: without a usable CUDA device tc_ctx_create fails
  *     with TC_E_NODEVICE and nothing else can be called.
  */
@@ -161,7 +163,9 @@ typedef struct {
 uint64_t tc_packed_bound(uint64_t n);
 /* tc_blocks_encode with container output: out[b] receives cap[b] >= tc_packed_bound(n[b]) bytes at
  * most, out_bytes[b] the size written.  Same pipelining; the packing runs on the device right
- * behind the RLE kernels. */
+ * behind the RLE kernels.  Up to 2 * lanes (at most 8) blocks have device-to-host copies pending at any
+ * time, so out[b] .. out[b + 7] must be distinct buffers (as must text[b] .. text[b + 7] if the caller
+ * refills them); all copies have completed when the call returns, also when it returns an error. */
 int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, const uint64_t *n, int with_mtf,
                             uint8_t *const *out, const uint64_t *cap, uint64_t *out_bytes, tc_block_info *info);
 /* Host-only (no device, no context): header check + tc_block_info of a container. */
@@ -235,6 +239,33 @@ int tc_fm_export(tc_ctx *ctx, const tc_fm *fm, int16_t *bwt /*N*/, uint32_t *sa_
  * image (NCCL) and re-open it on the peer with tc_fm_from_blob_dev. */
 const void *tc_fm_blob(const tc_fm *fm);
 int tc_fm_from_blob_dev(tc_ctx *ctx, void *d_blob, uint64_t bytes, int take_ownership, tc_fm **out);
+
+/* ---- multi-GPU below the C ABI ------------------------------------------------------------------
+ * The reference's only parallelism is parListChunk over the cores inside its ...P functions
+ * (src/Data/FMIndex.hs:417-423, 544-553): the LIBRARY CALL fans out.  These entry points do the same over the
+ * GPUs of one box from a single process (one host thread and one pooled context per device), so a caller
+ * that is not Python + torch.distributed gets all of them through one call.  devices[i] are CUDA ordinals. */
+int tc_device_count(void);
+/* The process-wide context of a device (created on first use, never destroyed): exclusive until released.
+ * For callers that would otherwise create and destroy a context per call (the Haskell shim's pure functions).
+ * Do not acquire the same device twice from one thread. */
+int tc_ctx_pool_acquire(int device, tc_ctx **out);
+void tc_ctx_pool_release(tc_ctx *ctx);
+/* tc_blocks_encode_packed over several devices (BASELINE.json config 5): block b runs on devices[b % ndev];
+ * independent blocks, no exchange step. */
+int tc_mgpu_blocks_encode_packed(int ndev, const int *devices, uint64_t nblocks, const uint8_t *const *text,
+                                 const uint64_t *n, int with_mtf, uint8_t *const *out, const uint64_t *cap,
+                                 uint64_t *out_bytes, tc_block_info *info);
+/* Copies the index image of `root` to devices[0 .. ndev) (peer copies over NVLink where the devices are peers)
+ * and opens it there: replicas[i] lives on devices[i] and is freed with tc_fm_free. */
+int tc_fm_replicate(const tc_fm *root, int ndev, const int *devices, tc_fm **replicas);
+/* tc_fm_count / tc_fm_locate with the q patterns split into ndev contiguous chunks (the reference's
+ * parListChunk), chunk i answered by replicas[i] on devices[i]; results in input order, exactly what the
+ * single-device calls return. */
+int tc_mgpu_fm_count(int ndev, const int *devices, tc_fm *const *replicas, const uint8_t *pats, const uint64_t *off,
+                     uint64_t q, int64_t *count);
+int tc_mgpu_fm_locate(int ndev, const int *devices, tc_fm *const *replicas, const uint8_t *pats, const uint64_t *off,
+                      uint64_t q, uint64_t *hit_off /*q+1*/, uint64_t *pos_1based, uint64_t cap, uint64_t *total);
 
 #ifdef __cplusplus
 }

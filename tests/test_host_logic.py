@@ -205,3 +205,102 @@ def test_stream_framing_host_side():
     for bad in (z[:10], z[:40], b"XXXX" + z[4:], z[:-1]):
         with pytest.raises(ValueError):
             stream.split_stream(bad)
+
+
+# ---- the Haskell boundary, as far as it can be checked without GHC --------------------------------------------
+def _hs_exports(path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("extract_exports", os.path.join(ROOT, "tests", "golden", "extract_exports.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.exports(path)
+
+
+def test_haskell_modules_keep_the_reference_export_lists():
+    """haskell/src/Data/{BWT,MTF,RLE,FMIndex}[/Internal].hs export exactly the names the reference modules export
+    (tests/golden/reference_exports.json, extracted from the reference by tests/golden/extract_exports.py);
+    Data.RLE.Internal adds one helper for its sibling modules."""
+    import json
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_exports.json")))
+    assert len(want) == 8
+    for mod, names in want.items():
+        path = os.path.join(ROOT, "haskell", "src", *mod.split(".")) + ".hs"
+        got_mod, got = _hs_exports(path)
+        assert got_mod == mod
+        extra = sorted(set(got) - set(names))
+        assert not (set(names) - set(got)), (mod, "missing", sorted(set(names) - set(got)))
+        assert extra == (["symbolBytes"] if mod == "Data.RLE.Internal" else []), (mod, extra)
+    # every exported function has a top-level type signature in the module
+    for mod in want:
+        src = open(os.path.join(ROOT, "haskell", "src", *mod.split(".")) + ".hs").read()
+        for name in want[mod]:
+            if name[0].islower() and "(" not in name:
+                assert re.search(r"^%s\s*::" % re.escape(name), src, re.M), (mod, name)
+
+
+def test_abi_layout_c99():
+    """tests/c/abi_layout.c: the struct offsets the Haskell shim reads (544 / 552 / 16) and every foreign import's
+    argument list, checked by gcc against include/tc_b200.h."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-c",
+                               os.path.join(ROOT, "tests", "c", "abi_layout.c"), "-o", os.path.join(d, "abi.o")])
+
+
+_HS2C = {"CInt": "i32", "Word32": "i32", "Int32": "i32", "Word64": "i64", "Int64": "i64", "CSize": "i64",
+         "CString": "ptr"}
+
+
+def _hs_kind(t):
+    t = t.strip()
+    if t == "()":
+        return "void"
+    if t.startswith("(") and t.endswith(")"):
+        t = t[1:-1].strip()
+    if t.startswith(("Ptr", "FunPtr")):
+        return "ptr"
+    return _HS2C[t]
+
+
+def _c_kind(t):
+    t = t.strip()
+    if "*" in t:
+        return "ptr"
+    t = re.sub(r"\b(const|unsigned)\b", "", t).split()
+    base = t[0] if t else "void"
+    return {"void": "void", "int": "i32", "uint32_t": "i32", "int32_t": "i32", "uint64_t": "i64", "int64_t": "i64",
+            "size_t": "i64"}[base]
+
+
+def test_foreign_imports_match_the_header():
+    """Every `foreign import ccall` in B200.hs against the prototype of the same name in include/tc_b200.h:
+    same arity, and per argument the same kind (pointer / 32-bit / 64-bit) in the same order."""
+    hs = open(os.path.join(ROOT, "haskell", "src", "Data", "TextCompression", "B200.hs")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tc_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([\w \*]+?)\b(tc_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        args = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        protos[name] = (_c_kind(ret), [_c_kind(re.sub(r"\b\w+$", "", a) if not a.endswith("*") else a) for a in args])
+    imports = re.findall(r'foreign import ccall \w+ "(&?)(tc_\w+)"\s*\n?\s*\w+\s*::\s*(.*?)(?=\nforeign import|\n\n|\n--)', hs, flags=re.S)
+    assert len(imports) >= 25
+    for amp, name, sig in imports:
+        assert name in protos, name
+        if amp:      # address import (finalisers): only the symbol must exist
+            continue
+        parts = [p.strip() for p in re.sub(r"\s+", " ", sig).split("->")]
+        res = re.sub(r"^IO\s*", "", parts[-1]).strip()
+        got = (_hs_kind(res), [_hs_kind(p) for p in parts[:-1]])
+        assert got == protos[name], (name, got, protos[name])
+
+
+def test_struct_offsets_used_by_the_shim():
+    """The byte offsets B200.hs hard-codes, against ctypes' layout of the same structs (which follows the C ABI)."""
+    from text_compression_b200._lib import BlockInfo, FmInfo
+    import ctypes as C
+    hs = open(os.path.join(ROOT, "haskell", "src", "Data", "TextCompression", "B200.hs")).read()
+    assert C.sizeof(BlockInfo) == 552 and BlockInfo.R.offset == 544
+    assert set(re.findall(r"peekByteOff pinfo (\d+)", hs)) == {"544"}
+    assert set(re.findall(r"pinned \((\d+) \* nb\)", hs)) == {"552"}
+    assert C.sizeof(FmInfo) == 2624 and FmInfo.C.offset == 552

@@ -101,6 +101,13 @@ _SIGS = {
     "tc_fm_export": (_int, [_vp, _vp, _vp, _vp]),
     "tc_fm_blob": (_vp, [_vp]),
     "tc_fm_from_blob_dev": (_int, [_vp, _vp, _u64, _int, C.POINTER(_vp)]),
+    "tc_device_count": (_int, []),
+    "tc_ctx_pool_acquire": (_int, [_int, C.POINTER(_vp)]),
+    "tc_ctx_pool_release": (None, [_vp]),
+    "tc_mgpu_blocks_encode_packed": (_int, [_int, _vp, _u64, _vp, _vp, _int, _vp, _vp, _vp, C.POINTER(BlockInfo)]),
+    "tc_fm_replicate": (_int, [_vp, _int, _vp, _vp]),
+    "tc_mgpu_fm_count": (_int, [_int, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "tc_mgpu_fm_locate": (_int, [_int, _vp, _vp, _vp, _vp, _u64, _vp, _vp, _u64, _pu64]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -16,6 +16,9 @@
     } while (0)
 
 namespace {
+// MTF recency keys are 32-bit distances (mtf.cu): N = n + 1 must stay below 2^31 - 1 when MTF takes part
+inline bool too_big(uint64_t n, bool with_mtf) { return n + 1 >= (with_mtf ? 0x7fffffffull : 0xfffffffeull); }
+
 template <typename T>
 int h2d(tc_ctx *ctx, T *dst, const T *src, size_t count) {
     if (count) TC_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
@@ -285,7 +288,7 @@ int compress_host(tc_ctx *ctx, const uint8_t *text, uint64_t n, bool with_mtf, u
     if (!info) return TC_E_ARG;
     info_clear(info, n);
     if (n == 0) return TC_OK;
-    if (n + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+    if (too_big(n, with_mtf)) return TC_E_TOOBIG;
     uint8_t *d_text;
     uint32_t *d_count;
     int16_t *d_rsym;
@@ -322,6 +325,17 @@ extern "C" int tc_bwt_mtf_rle_encode_dev(tc_ctx *ctx, const uint8_t *d_text, uin
 }
 
 namespace {
+// Every exit of a batch entry point -- errors included -- waits for the copies it has queued: the caller
+// frees or reuses text[] / out[] as soon as the call returns, and the next entry point hands out the arena
+// memory those copies touch.
+struct DrainGuard {
+    tc_ctx *c;
+    ~DrainGuard() {
+        if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+        if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+        cudaStreamSynchronize(c->stream);
+    }
+};
 // copy streams + events of the batch entry points (created on first use)
 int blocks_streams(tc_ctx *ctx) {
     if (ctx->s_h2d) return TC_OK;
@@ -346,10 +360,11 @@ extern "C" int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *co
     if (!text || !n || !count || !rsym || !cap || !info) return TC_E_ARG;
     uint64_t nmax = 0;
     for (uint64_t b = 0; b < nblocks; b++) {
-        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+        if (too_big(n[b], with_mtf != 0)) return TC_E_TOOBIG;
         nmax = n[b] > nmax ? n[b] : nmax;
     }
     TC_TRY(blocks_streams(ctx));
+    DrainGuard drain{ctx};
     const uint64_t worst = nmax + 3;
     uint8_t *d_text[2];
     uint32_t *d_count[2];
@@ -552,8 +567,19 @@ struct H2dChain {
 int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain, uint64_t nblocks, uint64_t nmax,
                        const uint8_t *const *text, const uint64_t *n, int with_mtf, uint8_t *const *out,
                        const uint64_t *cap, uint64_t *out_bytes, tc_block_info *info) {
+    TC_CUDA(cudaSetDevice(ctx->device)); // helper threads start on device 0
     TC_TRY(tc_ws_reset(ctx));
     TC_TRY(blocks_streams(ctx));
+    DrainGuard drain{ctx};
+    // an error in any lane stops the others at their next block: claiming past the end ends their loops
+    struct Abort {
+        std::atomic<uint64_t> &next;
+        uint64_t nblocks;
+        bool armed = true;
+        ~Abort() {
+            if (armed) next.store(nblocks);
+        }
+    } abort_others{next, nblocks};
     const uint64_t worst = nmax + 3;
     uint8_t *d_text[2];
     RlePack pk[2];
@@ -626,6 +652,7 @@ int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain
         d2h_pending[s] = true;
     }
     TC_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+    abort_others.armed = false;
     return rc_all;
 }
 } // namespace
@@ -675,7 +702,7 @@ extern "C" int tc_blocks_encode_packed(tc_ctx *ctx, uint64_t nblocks, const uint
     if (!text || !n || !out || !cap || !out_bytes || !info) return TC_E_ARG;
     uint64_t nmax = 0;
     for (uint64_t b = 0; b < nblocks; b++) {
-        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+        if (too_big(n[b], with_mtf != 0)) return TC_E_TOOBIG;
         nmax = n[b] > nmax ? n[b] : nmax;
         out_bytes[b] = 0;
     }
@@ -714,7 +741,7 @@ extern "C" int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t
     if (nblocks == 0) return TC_OK;
     if (!d_text || !n || !d_count || !d_rsym || !cap || !info) return TC_E_ARG;
     for (uint64_t b = 0; b < nblocks; b++)
-        if (n[b] + 1 >= 0xfffffffeull) return TC_E_TOOBIG;
+        if (too_big(n[b], with_mtf != 0)) return TC_E_TOOBIG;
     std::atomic<uint64_t> next{0};
     return run_lanes(ctx, nblocks, [&](tc_ctx *c) {
         return blocks_dev_lane(c, next, nblocks, d_text, n, with_mtf, d_count, d_rsym, cap, info);

@@ -42,7 +42,7 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     if (cudaSetDevice(device) != cudaSuccess) return TC_E_NODEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TC_E_NODEVICE;
-    if (prop.major < 10) return TC_E_NODEVICE; // kernels are compiled for sm_100a only
+    if (prop.major != 10 || prop.minor != 0) return TC_E_NODEVICE; // the cubin is sm_100a only: no image for any other part
     tc_ctx *ctx = new tc_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;

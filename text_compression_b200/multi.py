@@ -139,3 +139,101 @@ def build_replicated(ctx, d_text, n: int, sa_sample_rate: int = 32) -> Replicate
     torch.cuda.synchronize()
     ctx.call("tc_fm_from_blob_dev", C.c_void_p(img.data_ptr()), nbytes, 0, C.byref(h))
     return ReplicatedFM(ctx, h, img)
+
+
+# ---- single-process multi-GPU through the C ABI (tc_mgpu_*, tc_fm_replicate) -------------------------------
+# What a caller without torch.distributed gets (the Haskell shim's ...P functions): ONE library call fans out over
+# the GPUs of the box with a host thread and a pooled context per device.
+def device_count() -> int:
+    from ._lib import load
+    return int(load().tc_device_count())
+
+
+def _devs(devices):
+    devices = list(range(device_count())) if devices is None else list(devices)
+    return devices, (C.c_int * len(devices))(*devices)
+
+
+def compress_blocks_packed_multi(texts, with_mtf: bool = True, devices=None) -> list:
+    """tc_mgpu_blocks_encode_packed: block b runs on devices[b % len(devices)]; one container per block."""
+    from ._lib import BlockInfo, _raise, load, pinned_empty, TC_OK
+    from .seq import to_bytes
+    L = load()
+    devices, darr = _devs(devices)
+    ts = [np.ascontiguousarray(t if isinstance(t, np.ndarray) else np.frombuffer(to_bytes(t), dtype=np.uint8),
+                               dtype=np.uint8) for t in texts]
+    nb = len(ts)
+    if nb == 0:
+        return []
+    bound = [int(L.tc_packed_bound(t.size)) for t in ts]
+    outs = [pinned_empty(b, np.uint8) for b in bound]
+    ns = (C.c_uint64 * nb)(*[t.size for t in ts])
+    caps = (C.c_uint64 * nb)(*bound)
+    nbytes = (C.c_uint64 * nb)()
+    tp = (C.c_void_p * nb)(*[t.ctypes.data for t in ts])
+    op = (C.c_void_p * nb)(*[o.ctypes.data for o in outs])
+    infos = (BlockInfo * nb)()
+    rc = L.tc_mgpu_blocks_encode_packed(len(devices), darr, nb, tp, ns, 1 if with_mtf else 0, op, caps, nbytes, infos)
+    if rc != TC_OK:
+        _raise(None, rc)
+    return [outs[b][: int(nbytes[b])].copy() for b in range(nb)]
+
+
+class FMReplicas:
+    """One replica of an FM-index per device (tc_fm_replicate: peer copies of the image), queried with the
+    patterns split in contiguous chunks (tc_mgpu_fm_count / tc_mgpu_fm_locate); results in input order."""
+
+    def __init__(self, fm, devices=None):
+        from ._lib import _raise, load, TC_OK
+        self.L = load()
+        self.devices, self.darr = _devs(devices)
+        nd = len(self.devices)
+        self.reps = (C.c_void_p * nd)()
+        rc = self.L.tc_fm_replicate(fm.h, nd, self.darr, self.reps)
+        if rc != TC_OK:
+            _raise(None, rc)
+
+    def count_many(self, pats) -> np.ndarray:
+        from ._lib import _raise, ptr, TC_OK
+        from .fmindex import pack_patterns
+        flat, off = pack_patterns(pats)
+        q = off.size - 1
+        out = np.full(q, -1, dtype=np.int64)
+        if q:
+            rc = self.L.tc_mgpu_fm_count(len(self.devices), self.darr, self.reps, ptr(flat), ptr(off), q, ptr(out))
+            if rc != TC_OK:
+                _raise(None, rc)
+        return out
+
+    def locate_many(self, pats):
+        from ._lib import _raise, ptr, TC_E_CAP, TC_OK
+        from .fmindex import pack_patterns
+        flat, off = pack_patterns(pats)
+        q = off.size - 1
+        hit_off = np.zeros(q + 1, dtype=np.uint64)
+        total = C.c_uint64(0)
+        if q == 0:
+            return hit_off, np.empty(0, dtype=np.uint64)
+        nd = len(self.devices)
+        rc = self.L.tc_mgpu_fm_locate(nd, self.darr, self.reps, ptr(flat), ptr(off), q, ptr(hit_off), None, 0, C.byref(total))
+        if rc not in (TC_OK, TC_E_CAP):
+            _raise(None, rc)
+        pos = np.empty(int(total.value), dtype=np.uint64)
+        if pos.size:
+            rc = self.L.tc_mgpu_fm_locate(nd, self.darr, self.reps, ptr(flat), ptr(off), q, ptr(hit_off), ptr(pos), pos.size,
+                                          C.byref(total))
+            if rc != TC_OK:
+                _raise(None, rc)
+        return hit_off, pos
+
+    def close(self):
+        for i in range(len(self.devices)):
+            if self.reps[i]:
+                self.L.tc_fm_free(C.c_void_p(self.reps[i]))
+                self.reps[i] = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
