@@ -10,11 +10,11 @@ from .seq import BWT, MTF, RLE, MaybeSeq, TextBWT
 
 __version__ = "0.1.0"
 __all__ = ["Context", "default_context", "TcError", "FromJustError", "SeqIndexError", "NoDeviceError",
-           "BWT", "MTF", "RLE", "MaybeSeq", "TextBWT", "bwt", "mtf", "rle", "fmindex", "block", "stream"]
+           "BWT", "MTF", "RLE", "MaybeSeq", "TextBWT", "bwt", "mtf", "rle", "fmindex", "block", "stream", "generic", "multi"]
 
 
 def __getattr__(name):
-    if name in ("bwt", "mtf", "rle", "fmindex", "block", "multi", "stream"):
+    if name in ("bwt", "mtf", "rle", "fmindex", "block", "multi", "stream", "generic"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)
