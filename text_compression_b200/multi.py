@@ -25,21 +25,35 @@ def world():
 
 
 def bind_to_gpu_cpus(gpu_index: int) -> bool:
-    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity), so that pinned
-    host buffers are allocated on, and copied over, the GPU's own PCIe root / NUMA node.  One
-    process per GPU; call before allocating pinned memory.  Returns False if NVML is unavailable."""
+    """Pin this process to CPU cores next to its GPU (NVML's ideal affinity), so that pinned host buffers are
+    allocated on, and copied over, the GPU's own PCIe root / NUMA node.  When several GPUs report the SAME
+    affinity set (one NUMA node for all eight GPUs on the measured box: every rank and its three lane threads
+    landed on the same 32 cores), the set is cut into disjoint slices, one per GPU that shares it, so the
+    ranks' copy-issuing threads do not fight for the same cores.  One process per GPU; call before allocating
+    pinned memory.  Returns False if NVML is unavailable or nothing useful can be done."""
     import os
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
         ncpu = os.cpu_count() or 1
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
-        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
-        cpus &= set(os.sched_getaffinity(0))
-        if not cpus:
+        nw = (ncpu + 63) // 64
+        allowed = set(os.sched_getaffinity(0))
+
+        def affinity(i):
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), nw)
+            return frozenset({64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1} & allowed)
+
+        mine = affinity(gpu_index)
+        if not mine:
             return False
-        os.sched_setaffinity(0, cpus)
+        sharers = [i for i in range(pynvml.nvmlDeviceGetCount()) if affinity(i) == mine]
+        cpus = sorted(mine)
+        if len(sharers) > 1:
+            per = len(cpus) // len(sharers)
+            if per >= 4:                       # fewer than 4 cores per rank: leave the scheduler alone
+                j = sharers.index(gpu_index)
+                cpus = cpus[j * per:(j + 1) * per]
+        os.sched_setaffinity(0, set(cpus))
         return True
     except Exception:
         return False
