@@ -10,8 +10,18 @@ int bwt_decode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64
                            uint64_t cap, uint64_t *n_out);
 int bwt_decode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_bwt, uint64_t N, uint8_t *d_text, uint64_t cap,
                             uint64_t *n_out);
+// Run statistics handed from the MTF stage to the RLE stage of the composed helpers: the replay kernels hold the
+// indices in registers, so they count the run boundaries of their warp tiles on the way (mtf.cu RunStat) and the RLE
+// stage needs no counting pass over the index stream (rle.cu rle_emit_tiled_kernel).
+struct MtfRleLink {
+    uint4 *d_tstat = nullptr; // caller-allocated: ceil(N / 4096) records (a tile has at least 4096 symbols)
+    uint64_t ntiles = 0;      // set by the MTF stage
+    uint32_t tile_syms = 0;   // symbols per tile
+    bool valid = false;       // false: the MTF path taken does not collect them
+};
 int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
-                           int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint = nullptr);
+                           int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint = nullptr,
+                           MtfRleLink *link = nullptr);
 int mtf_finish_pending(tc_ctx *ctx); // see mtf.cu: deferred final list of the composed helpers
 void mtf_free_tables(tc_ctx *ctx);   // device tables of the small-alphabet automata
 int mtf_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint16_t *d_idx, int16_t *final_list,
@@ -31,7 +41,7 @@ struct RlePack {
 int rle_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint32_t *d_count,
                            int16_t *d_rsym, uint64_t cap, uint64_t *R, RlePack *pk = nullptr);
 int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
-                            uint64_t cap, uint64_t *R, RlePack *pk = nullptr);
+                            uint64_t cap, uint64_t *R, RlePack *pk = nullptr, const MtfRleLink *link = nullptr);
 int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt8, const uint8_t *d_sym8, const uint32_t *d_hi,
                         const uint64_t *d_big_idx, const uint32_t *d_big_cnt, uint64_t n_big, uint64_t R,
                         uint32_t *d_count, int16_t *d_rsym);

@@ -524,20 +524,26 @@ struct Present {
 };
 constexpr int TP_RLW = 131; // words per row of q values (257 u16 entries; odd, so rows start in different banks)
 
-// q[t][li] = 1 + offset of the last occurrence of li inside chunk t of the tile (0 = none), t = lane
+// A T-tile (the unit of T1 / T2 / T3) is TT_CH = 16 consecutive chunks: half the chain of dependent steps of a
+// 32-chunk tile in T3 and twice as many warps to hide its latencies.  In T1 two lanes scan one chunk, half each.
+constexpr int TT_CH = 16;
+// rows[2 c + h][li] = 1 + offset (inside chunk c of the tile) of the last occurrence of li in half h of the chunk
+// (0 = none); the chunk's value is the maximum of its two rows.  Lane l scans half l & 1 of chunk l >> 1.
 template <class Src>
 __device__ __forceinline__ void tile_positions(const Src &src, uint64_t N, uint32_t L, uint64_t nchunks, uint64_t tile,
                                                uint32_t *rows) {
     const unsigned lane = lane_id();
     for (int j = lane; j < 32 * TP_RLW; j += 32) rows[j] = 0;
     __syncwarp();
-    const uint64_t k = tile * 32 + lane;
-    if (k < nchunks) { // forward pass over the own chunk: later positions overwrite earlier ones
+    const uint64_t k = tile * TT_CH + (lane >> 1);
+    if (k < nchunks) { // forward pass over the own half chunk: later positions overwrite earlier ones
         uint16_t *row = reinterpret_cast<uint16_t *>(rows) + lane * (2 * TP_RLW);
-        const uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+        const uint64_t cbeg = k * L, cend = cbeg + L < N ? cbeg + L : N;
+        const uint64_t beg = cbeg + (lane & 1u) * (L / 2);              // L is a multiple of 32
+        const uint64_t end = (lane & 1u) ? cend : (cbeg + L / 2 < cend ? cbeg + L / 2 : cend);
         uint64_t pos = beg;
-        if (src.can_vec(beg)) {
-            // each lane streams its own chunk: keep 64 symbols' worth of loads in flight per lane
+        if (beg < end && src.can_vec(beg)) {
+            // each lane streams its own range: keep 64 symbols' worth of loads in flight per lane
             const uint64_t vend = beg + ((end - beg) & ~63ull);
             for (; pos < vend; pos += 64) {
                 typename Src::Raw raw[4];
@@ -547,13 +553,13 @@ __device__ __forceinline__ void tile_positions(const Src &src, uint64_t N, uint3
                 for (int b = 0; b < 4; b++) {
                     uint32_t li[16];
                     src.decode_li(raw[b], pos + 16 * b, li);
-                    const uint32_t o = (uint32_t)(pos - beg) + 16 * b + 1;
+                    const uint32_t o = (uint32_t)(pos - cbeg) + 16 * b + 1;
 #pragma unroll
                     for (int j = 0; j < 16; j++) row[li[j]] = (uint16_t)(o + j);
                 }
             }
         }
-        for (; pos < end; pos++) row[r3_lidx((uint32_t)src.at(pos))] = (uint16_t)(pos - beg + 1);
+        for (; pos < end; pos++) row[r3_lidx((uint32_t)src.at(pos))] = (uint16_t)(pos - cbeg + 1);
     }
     __syncwarp();
 }
@@ -569,22 +575,23 @@ __global__ void __launch_bounds__(T1_WARPS * 32)
     if (blockIdx.x == 0 && threadIdx.x == 0) *scan_ticket = 0; // for T2's "last CTA" election
     const unsigned lane = lane_id();
     const uint64_t tile = (uint64_t)blockIdx.x * T1_WARPS + (threadIdx.x >> 5);
-    if (tile * 32 >= nchunks) return;
+    if (tile * TT_CH >= nchunks) return;
     uint32_t *rows = smt1 + (threadIdx.x >> 5) * (32 * TP_RLW);
     tile_positions(src, N, L, nchunks, tile, rows);
     const uint16_t *q16 = reinterpret_cast<const uint16_t *>(rows);
-    const uint64_t tbase = tile * 32 * L;
-    const uint32_t nt = (uint32_t)(nchunks - tile * 32 < 32 ? nchunks - tile * 32 : 32);
+    const uint64_t tbase = tile * TT_CH * L;
+    const uint32_t nt = (uint32_t)(nchunks - tile * TT_CH < TT_CH ? nchunks - tile * TT_CH : TT_CH);
     uint32_t last[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) last[i] = 0;
 #pragma unroll 2
     for (uint32_t t = 0; t < nt; t++) {
-        uint16_t *out = start + (tile * 32 + t) * R3_ROW;
+        uint16_t *out = start + (tile * TT_CH + t) * R3_ROW;
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             const uint32_t li = lane + 32 * i;
-            const uint32_t q = li < SIGMAX ? q16[t * (2 * TP_RLW) + li] : 0u;
+            uint32_t q = 0;
+            if (li < SIGMAX) q = max((uint32_t)q16[(2 * t) * (2 * TP_RLW) + li], (uint32_t)q16[(2 * t + 1) * (2 * TP_RLW) + li]);
             out[li] = (uint16_t)q;
             if (q) last[i] = (t << 10) | q; // chunks ascend: the last one that saw the code wins
         }
@@ -696,7 +703,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32)
         return;
     }
     const uint64_t tile = (uint64_t)blockIdx.x * T3_WARPS + w;
-    if (tile * 32 >= nchunks) return;
+    if (tile * TT_CH >= nchunks) return;
     StartsWarp &W = sw[w];
     const unsigned lt = lanemask_lt();
     // list order at the start of the tile
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(T3_WARPS * 32)
             ord[i] = li == 256 ? 0u : li + 1u;
             tv[i] = valid[i] ? max(trow[tile * R3_ROW + li], segpre[(tile / seg_tiles) * R3_ROW + li]) : 0;
         }
-        list_positions_g(tv, valid, ord, tile * 32 * L, W.pro, lpos);
+        list_positions_g(tv, valid, ord, tile * TT_CH * L, W.pro, lpos);
 #pragma unroll
         for (int i = 0; i < 9; i++) { // the other entries: positions sigma .. 287, in any fixed order
             const unsigned b = __ballot_sync(TC_FULL, !valid[i]);
@@ -723,8 +730,8 @@ __global__ void __launch_bounds__(T3_WARPS * 32)
 #pragma unroll
     for (int j = 0; j < 16; j++) (&W.map8[0][0])[lane + 32 * j] = 0;
     __syncwarp();
-    const uint32_t nt = (uint32_t)(nchunks - tile * 32 < 32 ? nchunks - tile * 32 : 32);
-    uint16_t *row = start + tile * 32 * R3_ROW + lane;
+    const uint32_t nt = (uint32_t)(nchunks - tile * TT_CH < TT_CH ? nchunks - tile * TT_CH : TT_CH);
+    uint16_t *row = start + tile * TT_CH * R3_ROW + lane;
     // lane-rotated order in which a lane reads the 8 words (32 bytes) of its part of the byte map: no bank conflicts
     uint32_t woff[8], wsh[8];
 #pragma unroll
@@ -774,6 +781,37 @@ __global__ void __launch_bounds__(T3_WARPS * 32)
     }
 }
 
+// Run statistics of the index stream, collected by the replay kernels while the indices are in registers, so
+// that the RLE stage that follows in the composed helpers needs no pass of its own to count its runs
+// (rle.cu: rle_encode_tiled).  One record per warp tile (32 consecutive chunks):
+//   x = run boundaries inside the tile (positions whose index differs from the one before, the tile's first
+//       position not counted), y = 1 + position of the last of them (0 = none), z / w = first / last index.
+struct RunStat {
+    uint32_t npairs = 0, lhead = 0, first = 0, prev = 0xffffffffu;
+    __device__ __forceinline__ void see(uint32_t r, uint32_t pos) { // the chunk's first symbol counts as a boundary for now
+        const bool ne = r != prev;
+        npairs += ne;
+        if (ne) lhead = pos + 1;
+        if (prev == 0xffffffffu) first = r;
+        prev = r;
+    }
+    // all lanes of the warp; lane t holds chunk t of the tile (inactive lanes hold no chunk)
+    __device__ __forceinline__ void finish(bool active, uint32_t beg, uint64_t tile, uint4 *__restrict__ tstat) {
+        const unsigned lane = lane_id();
+        const uint32_t before = __shfl_up_sync(TC_FULL, prev, 1);
+        // a chunk start is a boundary only if the index differs from the last one of the chunk before; for the
+        // tile's first chunk that is decided by the scan over the tiles
+        if (active && npairs && (lane == 0 || first == before)) {
+            npairs--;
+            if (lhead == beg + 1) lhead = 0;
+        }
+        const uint32_t tp = __reduce_add_sync(TC_FULL, active ? npairs : 0u), th = __reduce_max_sync(TC_FULL, active ? lhead : 0u);
+        const unsigned act = __ballot_sync(TC_FULL, active);
+        const uint32_t tf = __shfl_sync(TC_FULL, first, 0), tl = __shfl_sync(TC_FULL, prev, 31 - __clz(act | 1u));
+        if (lane == 0 && act) tstat[tile] = make_uint4(tp, th, tf, tl);
+    }
+};
+
 struct R3 {
     uint16_t *last;  // per-thread base; entry li is li * CT halfwords further on
     uint32_t *bits;  // per-thread base; consecutive words are CT apart
@@ -809,16 +847,19 @@ __device__ __forceinline__ uint32_t r3_step(R3 &S, const uint64_t *m8tab, uint32
     return open ? inopen : closed;
 }
 
-template <class Src, int CT>
+template <class Src, int CT, bool RS>
 __global__ void __launch_bounds__(CT)
     mtf3_replay_kernel(Src src, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t sigma,
-                       const uint16_t *__restrict__ start, uint16_t *__restrict__ idx_out) {
+                       const uint16_t *__restrict__ start, uint16_t *__restrict__ idx_out, uint4 *__restrict__ tstat) {
     extern __shared__ __align__(16) uint32_t sm3[];
     __shared__ uint64_t m8tab[8];
     if (threadIdx.x < 8) m8tab[threadIdx.x] = 0x0001010101010101ull >> (56u - 8u * threadIdx.x); // bytes below kk
     __syncthreads();
     const uint64_t k = (uint64_t)blockIdx.x * CT + threadIdx.x;
-    if (k >= nchunks) return;
+    RunStat rs;
+    const bool active = k < nchunks;
+    if (!RS && !active) return;
+    if (active) { // (lanes without a chunk still take part in the warp reductions at the end)
     R3 S;
     S.last = reinterpret_cast<uint16_t *>(sm3) + threadIdx.x;
     S.bits = sm3 + R3_LASTW * CT + threadIdx.x;
@@ -910,6 +951,7 @@ __global__ void __launch_bounds__(CT)
                     }
                     const uint32_t r = r3_step<CT>(S, m8tab, a, (1u << j) << kb, 32u - j - kb);
                     o[j >> 1] = (j & 1) ? (o[j >> 1] | (r << 16)) : r;
+                    if (RS) rs.see(r, (uint32_t)pos + kb + j);
                 }
                 uint4 *dst = reinterpret_cast<uint4 *>(idx_out + pos + 16 * half);
                 dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -923,9 +965,13 @@ __global__ void __launch_bounds__(CT)
         const uint32_t li = r3_lidx((uint32_t)src.at(pos));
         const uint32_t a = S.last[li * CT];
         S.last[li * CT] = (uint16_t)(S.e0 + j);
-        idx_out[pos] = (uint16_t)r3_step<CT>(S, m8tab, a, 1u << j, 32u - j);
+        const uint32_t r = r3_step<CT>(S, m8tab, a, 1u << j, 32u - j);
+        idx_out[pos] = (uint16_t)r;
+        if (RS) rs.see(r, (uint32_t)pos);
         j = (j + 1) & 31u;
     }
+    } // active
+    if (RS) rs.finish(active, (uint32_t)(k * L), k >> 5, tstat);
 }
 
 // ---- encode, small alphabets (sigma <= 8: ACGT(N) + sentinel) -------------------------------------
@@ -1246,11 +1292,12 @@ __global__ void __launch_bounds__(AU_T, 4)
     if (threadIdx.x == AU_T - 1) tot[blockIdx.x] = summ_compose(pre, v);
 }
 
-template <class Src>
+template <class Src, bool RS>
 __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 16 MiB block are one wave
     mtfa_replay_kernel(Src src, AutoHash hs, uint64_t N, const uint16_t *__restrict__ g_perm,
                        const uint32_t *__restrict__ g_list, uint32_t n_perm, const Summ *__restrict__ part,
-                       const uint32_t *__restrict__ start_list, uint32_t sigma, uint16_t *__restrict__ idx_out) {
+                       const uint32_t *__restrict__ start_list, uint32_t sigma, uint16_t *__restrict__ idx_out,
+                       uint4 *__restrict__ tstat) {
     extern __shared__ __align__(16) uint32_t sma[];
     AutoSmem &A = *reinterpret_cast<AutoSmem *>(sma);
     auto_load_tables(A, g_perm, g_list, n_perm);
@@ -1263,6 +1310,8 @@ __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 
     const uint32_t full = (1u << sigma) - 1u;
     uint32_t st = 0;
     if (base < N) st = perm_rank(summ_compose(Summ{start_list[blockIdx.x], full}, part[chunk]).list, sigma) * (2 * AU_RW);
+    RunStat rs;
+    bool done = false;
     if constexpr (sizeof(*src.p) == 1) {
         if (wbase + 32 * AU_L <= N && src.can_vec(wbase) && (reinterpret_cast<uintptr_t>(idx_out + wbase) & 15) == 0) {
             const unsigned lane = lane_id();
@@ -1286,6 +1335,7 @@ __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 
                         const uint32_t x = e & 7u;
                         st = (e & 0xfff8u) >> 1;
                         o[k >> 1] = (k & 1) ? (o[k >> 1] | (x << 16)) : x;
+                        if (RS) rs.see(x, (uint32_t)base + 16 * (h * (AU_L / 32) + q) + k);
                     }
                     uint4 *dst = reinterpret_cast<uint4 *>(rows + lane * AU_ROW + 32 * q);
                     dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -1302,16 +1352,19 @@ __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 
                 }
                 __syncwarp();
             }
-            return;
+            done = true;
         }
     }
-    if (base >= N) return;
-    const uint64_t end = base + AU_L < N ? base + AU_L : N;
-    for (uint64_t pos = base; pos < end; pos++) {
-        const uint32_t e = *reinterpret_cast<const uint16_t *>(tab + st + hs.col2(r3_lidx((uint32_t)src.at(pos))));
-        idx_out[pos] = (uint16_t)(e & 7u);
-        st = (e & 0xfff8u) >> 1;
+    if (!done && base < N) {
+        const uint64_t end = base + AU_L < N ? base + AU_L : N;
+        for (uint64_t pos = base; pos < end; pos++) {
+            const uint32_t e = *reinterpret_cast<const uint16_t *>(tab + st + hs.col2(r3_lidx((uint32_t)src.at(pos))));
+            idx_out[pos] = (uint16_t)(e & 7u);
+            st = (e & 0xfff8u) >> 1;
+            if (RS) rs.see(e & 7u, (uint32_t)pos);
+        }
     }
+    if (RS) rs.finish(base < N, (uint32_t)base, chunk >> 5, tstat);
 }
 
 // ---- decode ----------------------------------------------------------------------------------
@@ -1671,8 +1724,9 @@ int auto_tables(tc_ctx *ctx, uint32_t sigma, const uint16_t *li_of_rank, AutoTab
 // knows it (the composed helpers do: a BWT has the symbols of its text plus the sentinel)
 template <class Src>
 int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *final_list, uint32_t *sigma_out,
-                    const uint8_t *present_hint = nullptr) {
+                    const uint8_t *present_hint = nullptr, MtfRleLink *link = nullptr) {
     *sigma_out = 0;
+    if (link) link->valid = false;
     if (N == 0) return TC_OK;
     if (N >= 0x7fffffffull) return TC_E_TOOBIG; // recency keys are 32-bit distances (see list_positions)
     WsMark mk = tc_ws_mark(ctx);
@@ -1719,7 +1773,8 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         const uint32_t abit = sizeof(*src.p) == 1 ? 4u : 8u;
         if (!(ctx->attr_done & abit)) {
             TC_CUDA(cudaFuncSetAttribute(mtfa_summary_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
-            TC_CUDA(cudaFuncSetAttribute(mtfa_replay_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+            TC_CUDA(cudaFuncSetAttribute(mtfa_replay_kernel<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
+            TC_CUDA(cudaFuncSetAttribute(mtfa_replay_kernel<Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sma));
             ctx->attr_done |= abit;
         }
         ctx->prof_bytes_next = N * sizeof(*src.p);
@@ -1727,8 +1782,14 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
                   part, tot);
         TC_LAUNCH(ctx, mtfs_top_kernel, 1, 1024, 0, tot, ntiles, sigma, start_list, d_final);
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
-        TC_LAUNCH(ctx, (mtfa_replay_kernel<Src>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list, at.n_perm,
-                  part, start_list, sigma, d_idx);
+        if (link) {
+            TC_LAUNCH(ctx, (mtfa_replay_kernel<Src, true>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list,
+                      at.n_perm, part, start_list, sigma, d_idx, link->d_tstat);
+            link->ntiles = ceil_div_u64(N, 32 * AU_L), link->tile_syms = 32 * AU_L, link->valid = true;
+        } else {
+            TC_LAUNCH(ctx, (mtfa_replay_kernel<Src, false>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list,
+                      at.n_perm, part, start_list, sigma, d_idx, (uint4 *)nullptr);
+        }
         *sigma_out = sigma;
         int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
         tc_ws_release(ctx, mk);
@@ -1760,7 +1821,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         if (ctx->mtf_L) Lt = ctx->mtf_L;
         Lt = (Lt + 31) / 32 * 32;
         const uint32_t L = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(Lt, 128), R3_LMAX);
-        const uint64_t nchunks = ceil_div_u64(N, L), ntiles = ceil_div_u64(nchunks, 32);
+        const uint64_t nchunks = ceil_div_u64(N, L), ntiles = ceil_div_u64(nchunks, TT_CH);
         uint32_t *trow, *finalocc;
         uint16_t *d_final, *start;
         TC_TRY(ws_alloc(ctx, ntiles * R3_ROW, &trow));
@@ -1784,7 +1845,9 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         const uint32_t abit = sizeof(*src.p) == 1 ? 1u : 2u;
         if (!(ctx->attr_done & abit)) {
             TC_CUDA(cudaFuncSetAttribute(mtf3_tile_last_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-            TC_CUDA(cudaFuncSetAttribute(mtf3_replay_kernel<Src, R3_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            TC_CUDA(cudaFuncSetAttribute(mtf3_replay_kernel<Src, R3_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem3));
+            TC_CUDA(cudaFuncSetAttribute(mtf3_replay_kernel<Src, R3_CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem3));
             ctx->attr_done |= abit;
         }
@@ -1795,8 +1858,14 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         TC_LAUNCH(ctx, mtf3_starts_kernel, (unsigned)ceil_div_u64(ntiles, T3_WARPS) + 1, T3_WARPS * 32, 0, pr, sigma, L,
                   nchunks, trow, segpre, seg_tiles, start, finalocc, N, d_final);
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
-        TC_LAUNCH(ctx, (mtf3_replay_kernel<Src, R3_CT>), (unsigned)ceil_div_u64(nchunks, R3_CT), R3_CT, smem3, src, N, L,
-                  nchunks, sigma, start, d_idx);
+        if (link) {
+            TC_LAUNCH(ctx, (mtf3_replay_kernel<Src, R3_CT, true>), (unsigned)ceil_div_u64(nchunks, R3_CT), R3_CT, smem3, src, N, L,
+                      nchunks, sigma, start, d_idx, link->d_tstat);
+            link->ntiles = ceil_div_u64(nchunks, 32), link->tile_syms = 32 * L, link->valid = true;
+        } else {
+            TC_LAUNCH(ctx, (mtf3_replay_kernel<Src, R3_CT, false>), (unsigned)ceil_div_u64(nchunks, R3_CT), R3_CT, smem3, src, N,
+                      L, nchunks, sigma, start, d_idx, (uint4 *)nullptr);
+        }
         *sigma_out = sigma;
         int rc = mtf_read_final(ctx, d_final, sigma, alpha_li, final_list, present_hint != nullptr, SIGMAX);
         tc_ws_release(ctx, mk);
@@ -1853,9 +1922,9 @@ int mtf_finish_pending(tc_ctx *ctx) {
 }
 
 int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
-                           int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint) {
+                           int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint, MtfRleLink *link) {
     if (N && primary >= N) primary = ~0ull;
-    return mtf_encode_impl(ctx, SrcU8{d_bwt, primary}, N, d_idx, final_list, sigma, present_hint);
+    return mtf_encode_impl(ctx, SrcU8{d_bwt, primary}, N, d_idx, final_list, sigma, present_hint, link);
 }
 int mtf_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint16_t *d_idx, int16_t *final_list,
                                uint32_t *sigma) {

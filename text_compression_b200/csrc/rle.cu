@@ -192,11 +192,15 @@ struct PackArgs { // device pointers of RlePack, passed by value to the emit ker
     unsigned long long *n_big;
 };
 
+// One tile of RT * ITEMS positions starting at tile_base (those below lim_end <= N): goff = runs emitted before it,
+// Hx / Jx = latest head / latest Just before it.  Returns the tile's run count and its latest head (for callers that walk several
+// tiles in one CTA).  All threads of the CTA must call.
 template <class In, bool PACKED>
-__global__ void __launch_bounds__(RT)
-    rle_emit_kernel(In in, uint64_t N, const uint64_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_headx,
-                    const uint32_t *__restrict__ tile_justx, uint32_t *__restrict__ count, int16_t *__restrict__ rsym,
-                    uint64_t cap, uint64_t *__restrict__ d_R, PackArgs pk) {
+__device__ __forceinline__ void rle_emit_tile(In in, uint64_t N, uint64_t lim_end, uint64_t tile_base, uint64_t goff, uint32_t Hx,
+                                              uint32_t Jx,
+                                              uint32_t *__restrict__ count, int16_t *__restrict__ rsym, uint64_t cap,
+                                              uint64_t *__restrict__ d_R, PackArgs pk, bool last_tile, uint32_t *out_total,
+                                              uint32_t *out_head) {
     constexpr int ITEMS = In::ITEMS;
     // + one Nothing's second pair + final flush + alignment pad, rounded up to the swizzle period
     constexpr int CAP = (In::MAX_PER_ITEM * RT * ITEMS + 3 + 8 + 63) / 64 * 64;
@@ -205,7 +209,6 @@ __global__ void __launch_bounds__(RT)
     __shared__ __align__(16) int16_t s_sym_raw[CAP];
     // runs are staged so that staged index and global index agree modulo the vector width:
     // the copy-out below then moves 16 bytes per store
-    const uint64_t goff = tile_off[blockIdx.x];
     const uint32_t padc = (uint32_t)(goff & 3), pads = (uint32_t)(goff & 7);
     // A thread writes its (up to 16) runs to consecutive slots, so the lanes of a warp hit slots 16
     // apart: 2 banks for 32 lanes.  XOR-ing two slot bits with the thread's position spreads them
@@ -242,13 +245,14 @@ __global__ void __launch_bounds__(RT)
             s_sym_raw[ps(slot)] = (int16_t)sym;
         }
     };
-    uint64_t base = ((uint64_t)blockIdx.x * RT + threadIdx.x) * ITEMS;
+    uint64_t base = tile_base + (uint64_t)threadIdx.x * ITEMS;
     int c[ITEMS];
     int p0 = NOPREV;
     uint32_t pairs = 0, lh = 0, lj = 0;
     const uint32_t b32 = (uint32_t)base;
-    const int lim = base >= N ? 0 : (base + ITEMS <= N ? ITEMS : (int)(N - base));
-    if (base < N) {
+    const int lim = base >= lim_end ? 0 : (base + ITEMS <= lim_end ? ITEMS : (int)(lim_end - base));
+    const bool owns_last = lim > 0 && base + lim == N; // this thread holds position N-1
+    if (lim > 0) {
         in.load(base, N, c);
         p0 = base == 0 ? NOPREV : in.at(base - 1);
         int p = p0;
@@ -270,18 +274,19 @@ __global__ void __launch_bounds__(RT)
                 p = c[k];
             }
         }
-        if (base + ITEMS >= N) pairs += 1; // this thread owns position N-1: final flush
+        if (owns_last) pairs += 1; // final flush
     }
-    uint32_t tile_total;
+    uint32_t tile_total, head_total;
     uint32_t o = block_excl_sum<uint32_t, RT>(pairs, sh, &tile_total);
-    uint32_t H = block_excl_max<uint32_t, RT>(lh, 0u, sh, (uint32_t *)nullptr);
+    uint32_t H = block_excl_max<uint32_t, RT>(lh, 0u, sh, &head_total);
     uint32_t J = 0;
     if (In::HAS_NOTHING) J = block_excl_max<uint32_t, RT>(lj, 0u, sh, (uint32_t *)nullptr);
-    H = max(H, tile_headx[blockIdx.x]);
-    if (In::HAS_NOTHING) J = max(J, tile_justx[blockIdx.x]);
-    if (base < N) {
+    H = max(H, Hx);
+    if (In::HAS_NOTHING) J = max(J, Jx);
+    *out_total = tile_total;
+    *out_head = max(head_total, Hx);
+    if (lim > 0) {
         int p = p0;
-        const bool owns_last = base + ITEMS >= N; // this thread holds position N-1
 #pragma unroll
         for (int k = 0; k < ITEMS; k++) {
             if (k < lim) {
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(RT)
                 else if (word) atomicOr(&pk.hi[(gp >> 5) + v], word);
             }
         }
-        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;
+        if (last_tile && threadIdx.x == 0) *d_R = goff + tile_total;
         return;
     }
     const bool vec_ok = goff + tile_total <= cap && (reinterpret_cast<uintptr_t>(count) & 15) == 0 &&
@@ -389,7 +394,87 @@ __global__ void __launch_bounds__(RT)
             }
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *d_R = goff + tile_total;
+    if (last_tile && threadIdx.x == 0) *d_R = goff + tile_total;
+}
+
+template <class In, bool PACKED>
+__global__ void __launch_bounds__(RT)
+    rle_emit_kernel(In in, uint64_t N, const uint64_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_headx,
+                    const uint32_t *__restrict__ tile_justx, uint32_t *__restrict__ count, int16_t *__restrict__ rsym,
+                    uint64_t cap, uint64_t *__restrict__ d_R, PackArgs pk) {
+    uint32_t tt, th;
+    rle_emit_tile<In, PACKED>(in, N, N, (uint64_t)blockIdx.x * RT * In::ITEMS, tile_off[blockIdx.x], tile_headx[blockIdx.x],
+                              In::HAS_NOTHING ? tile_justx[blockIdx.x] : 0u, count, rsym, cap, d_R, pk,
+                              blockIdx.x == gridDim.x - 1, &tt, &th);
+}
+
+// ---- runs of an MTF index stream whose statistics the MTF replay kernel collected (mtf.cu RunStat) --------------
+// tstat[T] = (run boundaries inside MTF tile T, 1 + position of the last one, first index, last index).  One CTA:
+// the boundary at the start of every tile is decided here (first index against the last index of the tile before),
+// then exclusive sum of the runs and exclusive max of the heads over the tiles.
+__global__ void __launch_bounds__(1024)
+    rle_tstat_scan_kernel(const uint4 *__restrict__ tstat, uint64_t ntiles, uint32_t tile_syms, uint64_t *__restrict__ toff,
+                          uint32_t *__restrict__ theadx) {
+    __shared__ uint64_t sh64[1024 / 32 + 1];
+    __shared__ uint32_t sh32[1024 / 32 + 1];
+    uint64_t carry = 0;
+    uint32_t ch = 0;
+    for (uint64_t b = 0; b < ntiles; b += 1024 * 4) {
+        const uint64_t t0 = b + (uint64_t)threadIdx.x * 4;
+        uint32_t p[4], h[4];
+        uint64_t v = 0;
+        uint32_t hm = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t t = t0 + q;
+            p[q] = h[q] = 0;
+            if (t < ntiles) {
+                const uint4 me = tstat[t];
+                const bool starts = t == 0 || me.z != tstat[t - 1].w; // a run starts at the tile's first position
+                p[q] = me.x + (t > 0 && starts);
+                h[q] = max(me.y, starts ? (uint32_t)(t * tile_syms) + 1u : 0u);
+            }
+            v += p[q];
+            hm = max(hm, h[q]);
+        }
+        uint64_t tot;
+        uint32_t th;
+        uint64_t ex = carry + block_excl_sum<uint64_t, 1024>(v, sh64, &tot);
+        uint32_t hx = max(ch, block_excl_max<uint32_t, 1024>(hm, 0u, sh32, &th));
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (t0 + q < ntiles) {
+                toff[t0 + q] = ex;
+                theadx[t0 + q] = hx;
+            }
+            ex += p[q];
+            hx = max(hx, h[q]);
+        }
+        carry += tot;
+        ch = max(ch, th);
+    }
+}
+
+// CTA per MTF tile: its tile_syms positions in sub-tiles of RT * ITEMS, run offset and latest head carried along
+template <class In, bool PACKED>
+__global__ void __launch_bounds__(RT)
+    rle_emit_tiled_kernel(In in, uint64_t N, uint32_t tile_syms, const uint64_t *__restrict__ toff,
+                          const uint32_t *__restrict__ theadx, uint32_t *__restrict__ count, int16_t *__restrict__ rsym,
+                          uint64_t cap, uint64_t *__restrict__ d_R, PackArgs pk) {
+    constexpr uint32_t SUB = RT * In::ITEMS;
+    const uint64_t t_beg = (uint64_t)blockIdx.x * tile_syms, t_end = t_beg + tile_syms < N ? t_beg + tile_syms : N;
+    uint64_t goff = toff[blockIdx.x];
+    uint32_t H = theadx[blockIdx.x];
+    for (uint64_t sb = t_beg; sb < t_end; sb += SUB) {
+        uint32_t tt, th;
+        // (only the sub-tile that holds position N - 1 flushes the last run and writes R; the packed path returns
+        // from the tile function early, so the barrier below is reached by all threads either way)
+        rle_emit_tile<In, PACKED>(in, N, t_end, sb, goff, H, 0u, count, rsym, cap, d_R, pk, t_end == N && sb + SUB >= N, &tt,
+                                  &th);
+        goff += tt;
+        H = th;
+        __syncthreads();
+    }
 }
 
 // ---- packed run payload (block container) ------------------------------------
@@ -438,12 +523,13 @@ int rle_sort_big(tc_ctx *ctx, RlePack *pk) {
 
 template <class In>
 int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *d_rsym, uint64_t cap, uint64_t *R,
-                    RlePack *pk = nullptr) {
+                    RlePack *pk = nullptr, const MtfRleLink *link = nullptr) {
     *R = 0;
     if (N == 0) return TC_OK;
     if (N >= 0xfffffffeull) return TC_E_TOOBIG;
     constexpr uint64_t TILE = (uint64_t)RT * In::ITEMS;
-    uint64_t tiles = ceil_div_u64(N, TILE);
+    const bool tiled = link && link->valid && !In::HAS_NOTHING; // the MTF stage counted the runs of its tiles already
+    uint64_t tiles = tiled ? link->ntiles : ceil_div_u64(N, TILE);
     WsMark mk = tc_ws_mark(ctx);
     uint32_t *tp, *th, *tj;
     uint64_t *toff, *d_R;
@@ -452,21 +538,36 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
     TC_TRY(ws_alloc(ctx, tiles, &tj));
     TC_TRY(ws_alloc(ctx, tiles, &toff));
     TC_TRY(ws_alloc(ctx, 2, &d_R));
-    TC_LAUNCH(ctx, (rle_reduce_kernel<In>), (unsigned)tiles, RT, 0, in, N, tp, th, tj);
-    // NB: the reduce kernel's tile pair counts exclude the final flush; the emit kernel adds it
-    // for the owner of position N-1, which is always in the last tile, so offsets stay exact.
-    TC_LAUNCH(ctx, rle_tile_scan_kernel, 1, 1024, 0, tp, th, tj, toff, tiles);
+    if (tiled) {
+        TC_LAUNCH(ctx, rle_tstat_scan_kernel, 1, 1024, 0, link->d_tstat, tiles, link->tile_syms, toff, th);
+    } else {
+        TC_LAUNCH(ctx, (rle_reduce_kernel<In>), (unsigned)tiles, RT, 0, in, N, tp, th, tj);
+        // NB: the reduce kernel's tile pair counts exclude the final flush; the emit kernel adds it
+        // for the owner of position N-1, which is always in the last tile, so offsets stay exact.
+        TC_LAUNCH(ctx, rle_tile_scan_kernel, 1, 1024, 0, tp, th, tj, toff, tiles);
+    }
+    PackArgs pa{};
     if (pk) {
         // d_R and the exception counter sit next to each other so that one small copy brings both back
         pk->n_big = 0;
         TC_CUDA(cudaMemsetAsync(d_R + 1, 0, sizeof(uint64_t), ctx->stream));
         TC_CUDA(cudaMemsetAsync(pk->hi, 0, ceil_div_u64(cap, 32) * sizeof(uint32_t), ctx->stream));
-        PackArgs pa{pk->cnt8, pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap, (unsigned long long *)(d_R + 1)};
+        pa = PackArgs{pk->cnt8, pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap, (unsigned long long *)(d_R + 1)};
+    }
+    ctx->prof_bytes_next = N * sizeof(*in.p);
+    if (tiled) {
+        if (pk)
+            TC_LAUNCH(ctx, (rle_emit_tiled_kernel<In, true>), (unsigned)tiles, RT, 0, in, N, link->tile_syms, toff, th, d_count,
+                      d_rsym, cap, d_R, pa);
+        else
+            TC_LAUNCH(ctx, (rle_emit_tiled_kernel<In, false>), (unsigned)tiles, RT, 0, in, N, link->tile_syms, toff, th, d_count,
+                      d_rsym, cap, d_R, pa);
+    } else if (pk) {
         TC_LAUNCH(ctx, (rle_emit_kernel<In, true>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap, d_R,
                   pa);
     } else {
         TC_LAUNCH(ctx, (rle_emit_kernel<In, false>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap,
-                  d_R, PackArgs{});
+                  d_R, pa);
     }
     TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, (pk ? 2 : 1) * sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -565,8 +666,8 @@ int rle_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64
     return rle_encode_impl(ctx, InU8{d_bwt, primary}, N, d_count, d_rsym, cap, R, pk);
 }
 int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
-                            uint64_t cap, uint64_t *R, RlePack *pk) {
-    return rle_encode_impl(ctx, In16<false>{d_idx}, N, d_count, d_rsym, cap, R, pk);
+                            uint64_t cap, uint64_t *R, RlePack *pk, const MtfRleLink *link) {
+    return rle_encode_impl(ctx, In16<false>{d_idx}, N, d_count, d_rsym, cap, R, pk, link);
 }
 int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt8, const uint8_t *d_sym8, const uint32_t *d_hi,
                         const uint64_t *d_big_idx, const uint32_t *d_big_cnt, uint64_t n_big, uint64_t R,
