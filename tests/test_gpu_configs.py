@@ -212,3 +212,34 @@ def test_mtf_kernels_agree(ctx, orc):
                     _same(f"indices n={n} sigma={sigma} {mode} primary={primary}", idx, o_idx)
                     _same("final list", fin[: sg.value], o_fin)
     ctx2.close()
+
+
+def test_raw_byte_keys_vs_oracle(ctx, orc):
+    """Equiprobable bytes take the leading-bytes uniform key (sufsort.cu uk_keys_raw_kernel): 4 MiB + 3 of random bytes
+    (odd length: the last suffixes read past the end), against the oracle and against the arithmetic-code keys
+    (TC_B200_NO_RAWKEY=1); and a text whose byte histogram is flat but which repeats a 4 KiB block (every key
+    ties: the general path must take over)."""
+    import os
+    from text_compression_b200 import _lib
+    from text_compression_b200._lib import ptr
+    os.environ["TC_B200_NO_RAWKEY"] = "1"
+    try:
+        ctx2 = _lib.Context(0)
+    finally:
+        del os.environ["TC_B200_NO_RAWKEY"]
+    rng = np.random.default_rng(5)
+    blk = np.repeat(np.arange(256, dtype=np.uint8), 16)
+    rng.shuffle(blk)
+    texts = [gen_bytes(77, (4 << 20) + 3), np.tile(blk, 300)[: 300 * 4096 - 5]]
+    for t in texts:
+        o_bwt, o_sa = orc.bwt_encode(t, want_sa=True)
+        for c in (ctx, ctx2):
+            bwt = np.empty(t.size + 1, dtype=np.uint8)
+            sa = np.empty(t.size + 1, dtype=np.uint32)
+            primary = C.c_uint64(0)
+            c.call("tc_bwt_encode", ptr(t), t.size, ptr(bwt), C.byref(primary), ptr(sa))
+            _same("suffix array", sa, o_sa)
+            g = bwt.astype(np.int16)
+            g[primary.value] = -1
+            _same("bwt", g, o_bwt)
+    ctx2.close()

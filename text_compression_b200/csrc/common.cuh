@@ -48,6 +48,7 @@ struct tc_ctx {
     tc_ctx *child[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
     int lanes = 3; // blocks in flight per call (TC_B200_LANES=1..4; measured 2: 18.8, 3: 19.6, 4: 19.8 GB/s on C2)
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
+    bool no_rawkey = false; // TC_B200_NO_RAWKEY=1: arithmetic-code uniform keys also for equiprobable bytes (tests compare both)
     bool mtf_v2 = false; // TC_B200_MTF_V2=1: warp-per-chunk MTF replay (the round-1 kernel) instead of thread-per-chunk
     uint32_t mtf_L = 0;  // TC_B200_MTF_L: chunk length of the thread-per-chunk MTF replay (0 = one chunk per resident thread)
     void *mtf_auto[9] = {nullptr}; // per alphabet size: device tables of the MTF automata (mtf.cu: AutoTables)

@@ -48,6 +48,8 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     ctx->sm_count = prop.multiProcessorCount;
     const char *nm = getenv("TC_B200_NO_MSD");
     ctx->no_msd = nm && nm[0] == '1';
+    const char *nr = getenv("TC_B200_NO_RAWKEY");
+    ctx->no_rawkey = nr && nr[0] == '1';
     const char *m2 = getenv("TC_B200_MTF_V2");
     ctx->mtf_v2 = m2 && m2[0] == '1';
     const char *ml = getenv("TC_B200_MTF_L");

@@ -279,6 +279,58 @@ __global__ void __launch_bounds__(PC_T, 3)
     if (s) atomicAdd(&hist1[threadIdx.x], s);
 }
 
+// K_A for (nearly) equiprobable bytes -- already compressed, encrypted or random data: with all 256 byte values
+// equally likely the arithmetic code of a suffix IS its leading bytes, so the uniform key is the big-endian word
+// text[i .. i+3] (zeros past the end; ties fall to the packed keys as always) and no table walk is needed.
+__global__ void __launch_bounds__(PC_T, 3)
+    uk_keys_raw_kernel(const uint8_t *__restrict__ t, uint32_t n, int shift1, uint32_t *__restrict__ ukey,
+                       uint32_t *__restrict__ hist1) {
+    extern __shared__ __align__(16) uint8_t pc_cnt[];
+    __shared__ uint16_t wtot[PC_WARPS][256];
+    const int w = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    uint8_t *wc = pc_cnt + (size_t)w * 8192;
+    pc_zero(wc, lane);
+    __syncthreads();
+    const uint32_t tbase = blockIdx.x * PC_TILE + w * PC_WCHUNK;
+    uint8_t *mine = wc + lane;
+    const bool aligned = (reinterpret_cast<uintptr_t>(t) & 3) == 0;
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(t);
+    for (int r0 = 0; r0 < PC_ITEMS; r0 += 8) {
+        uint32_t w0[8], w1[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t i = tbase + (r0 + q) * 32 + lane;
+            const bool fast = aligned && i + 8 <= n; // both words inside the text
+            w0[q] = fast ? t32[i >> 2] : 0u;
+            w1[q] = fast ? t32[(i >> 2) + 1] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t i = tbase + (r0 + q) * 32 + lane;
+            if (i < n) {
+                uint32_t u;
+                if (aligned && i + 8 <= n) {
+                    u = __byte_perm(w0[q], w1[q], 0x0123u + 0x1111u * (i & 3u));
+                } else {
+                    u = 0;
+                    for (int k = 0; k < 4; k++) u = (u << 8) | (i + k < n ? (uint32_t)t[i + k] : 0u);
+                }
+                ukey[i] = u;
+                mine[(u >> shift1) * 32]++;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) wtot[w][q * 32 + lane] = (uint16_t)pc_total(wc, q, lane);
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int ww = 0; ww < PC_WARPS; ww++) s += wtot[ww][threadIdx.x];
+    if (s) atomicAdd(&hist1[threadIdx.x], s);
+}
+
 // Partition tiles never straddle a segment (= a bucket of the previous level).  tilebase[s]
 // = first tile of segment s, chunkbase[s] = first counting chunk of segment s.
 constexpr int PT_T = 256;
@@ -899,10 +951,20 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         TC_CUDA(cudaFuncSetAttribute(seg_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
         TC_CUDA(cudaFuncSetAttribute(part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
         TC_CUDA(cudaFuncSetAttribute(part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtSmem)));
-        TC_LAUNCH(ctx, uk_lut_kernel, 1, 1024, 0, sp, sigma, b, gs, uk_lut);
+        // equiprobable bytes (every value within 5 % of n / 256): the leading bytes are the uniform key
+        bool flat = sigma == 256 && !ctx->no_rawkey;
+        for (int c = 0; c < 256 && flat; c++) flat = fabs((double)hist[c] * 256.0 / (double)n - 1.0) < 0.05;
         ctx->prof_bytes_next = n + 4 * n;
-        TC_LAUNCH_AS(ctx, "uk_keys_kernel", kkeys, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut, (uint32_t)n,
-                  B1 ? 32 - B1 : 31, ukey, hist1);
+        if (flat) {
+            TC_CUDA(cudaFuncSetAttribute(uk_keys_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+            TC_LAUNCH(ctx, uk_keys_raw_kernel, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, d_text, (uint32_t)n,
+                      B1 ? 32 - B1 : 31, ukey, hist1);
+        } else {
+            TC_LAUNCH(ctx, uk_lut_kernel, 1, 1024, 0, sp, sigma, b, gs, uk_lut);
+            ctx->prof_bytes_next = n + 4 * n;
+            TC_LAUNCH_AS(ctx, "uk_keys_kernel", kkeys, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut,
+                         (uint32_t)n, B1 ? 32 - B1 : 31, ukey, hist1);
+        }
         TC_LAUNCH(ctx, seg_tables_kernel, 1, 256, 0, hist1, nb1, segstart, cursor1, tilebase, chunkbase);
         ctx->prof_bytes_next = 4 * n + (packprev ? n : 0) + 8 * n;
         TC_LAUNCH(ctx, part_kernel<true>, (unsigned)ceil_div_u64(n, PT_TILE), PT_T, sizeof(PtSmem), ukey, d_text, packprev,
