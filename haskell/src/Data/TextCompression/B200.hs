@@ -113,7 +113,7 @@ foreign import ccall safe "tc_bwt_mtf_rle_encode"
 foreign import ccall safe "tc_blocks_encode"
   c_blocks_encode :: Ptr TcCtx -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> CInt -> Ptr (Ptr Word32)
                   -> Ptr (Ptr Int16) -> Ptr Word64 -> Ptr () -> IO CInt
--- same, with one packed block container per block as output (tc_packed_header + cnt8 / sym8 / hi
+-- same, with one packed block container per block as output (tc_packed_header + cnt4 / sym8 / hi
 -- sections): a third of the bytes over PCIe, and a single ByteString per block on the Haskell side
 foreign import ccall safe "tc_packed_bound" c_packed_bound :: Word64 -> IO Word64
 foreign import ccall safe "tc_blocks_encode_packed"

@@ -137,23 +137,23 @@ int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *const *text, 
 /* ---- packed block container (the reference has only Show/Read,
  * src/Data/RLE/Internal.hs:95-96, src/Data/MTF/Internal.hs:67-68) --------------------
  * One compressed block as a single little-endian byte string: the tc_block_info fields, then the
- * runs at 2 bytes + 1 bit each instead of the 6-byte (count, symbol) record, so a stream of blocks
- * moves a third of the bytes over PCIe:
- *   cnt8[R]   min(count, 255)
+ * runs at 1.625 bytes each instead of the 6-byte (count, symbol) record, so a stream of blocks
+ * moves a quarter of the bytes over PCIe (version 2; version 1 spent a whole byte per count):
+ *   cnt4[ceil(R/2)]  min(count - 1, 15) in four bits per run, run k in bits 4 (k % 2) .. of byte k / 2
  *   sym8[R]   low byte of the symbol's 9-bit code (code = symbol & 0x1ff: MTF indices 0..256 as
  *             they are, BWT symbols 0..255 as they are, Nothing = 0x1ff)
  *   hi[ceil(R/32)] u32 words, bit k%32 of word k/32 = bit 8 of run k's code
- *   big_idx[n_big] u64, big_cnt[n_big] u32: the runs whose count is >= 255, ascending run index
+ *   big_idx[n_big] u64, big_cnt[n_big] u32: the runs whose count is >= 16 (nibble 15), ascending run index
  * Sections start at the 16-byte-aligned offsets the header states.  The container is lossless for
  * the run sequence: tc_packed_unpack gives back exactly what tc_blocks_encode returns. */
 #define TC_PACKED_MAGIC 0x314b4c4242434254ull /* "TCBBLK1" */
 #define TC_PACKED_MTF 1u                      /* flags bit 0: runs are over the MTF index stream */
 typedef struct {
     uint64_t magic;
-    uint32_t version; /* 1 */
+    uint32_t version; /* 2 */
     uint32_t flags;
     uint64_t n, N, primary, R, n_big, total_bytes;
-    uint64_t off_cnt8, off_sym8, off_hi, off_big_idx, off_big_cnt; /* from the start of the container */
+    uint64_t off_cnt4, off_sym8, off_hi, off_big_idx, off_big_cnt; /* from the start of the container */
     uint32_t sigma;
     uint32_t reserved;
     int16_t final_list[257];

@@ -22,7 +22,7 @@ SA(sizeof(tc_block_info) == 552, "sizeof tc_block_info (B200.hs: pinned (552 * n
 SA(offsetof(tc_packed_header, magic) == 0, "tc_packed_header.magic");
 SA(offsetof(tc_packed_header, n) == 16, "tc_packed_header.n (B200.hs: peekByteOff p 16)");
 SA(offsetof(tc_packed_header, R) == 40, "tc_packed_header.R");
-SA(offsetof(tc_packed_header, off_cnt8) == 64, "tc_packed_header.off_cnt8");
+SA(offsetof(tc_packed_header, off_cnt4) == 64, "tc_packed_header.off_cnt4");
 SA(offsetof(tc_packed_header, final_list) == 112, "tc_packed_header.final_list");
 SA(sizeof(tc_packed_header) == 640, "sizeof tc_packed_header");
 /* tc_fm_info (text_compression_b200/_lib.py FmInfo mirrors it) */

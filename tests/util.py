@@ -49,10 +49,10 @@ def pack_container(n, N, primary, sigma, final_list, counts, syms, with_mtf) -> 
     counts = np.asarray(counts, dtype=np.uint32)
     syms = np.asarray(syms, dtype=np.int16)
     R = int(counts.size)
-    big = np.nonzero(counts >= 255)[0].astype(np.uint64)
+    big = np.nonzero(counts >= 16)[0].astype(np.uint64)
     al = lambda x: (x + 15) & ~15
-    off_cnt8 = 640
-    off_sym8 = al(off_cnt8 + R)
+    off_cnt4 = 640
+    off_sym8 = al(off_cnt4 + (R + 1) // 2)
     off_hi = al(off_sym8 + R)
     off_big_idx = al(off_hi + (R + 31) // 32 * 4)
     off_big_cnt = al(off_big_idx + 8 * big.size)
@@ -60,12 +60,14 @@ def pack_container(n, N, primary, sigma, final_list, counts, syms, with_mtf) -> 
     out = np.zeros(total, dtype=np.uint8)
     fl = np.zeros(257 + 7, dtype=np.int16)
     fl[: len(final_list)] = np.asarray(final_list, dtype=np.int16)
-    hdr = struct.pack("<QII6Q5QII", 0x314B4C4242434254, 1, 1 if with_mtf else 0, n, N, primary, R, int(big.size), total,
-                      off_cnt8, off_sym8, off_hi, off_big_idx, off_big_cnt, sigma, 0) + fl.tobytes()
+    hdr = struct.pack("<QII6Q5QII", 0x314B4C4242434254, 2, 1 if with_mtf else 0, n, N, primary, R, int(big.size), total,
+                      off_cnt4, off_sym8, off_hi, off_big_idx, off_big_cnt, sigma, 0) + fl.tobytes()
     assert len(hdr) == 640
     out[:640] = np.frombuffer(hdr, dtype=np.uint8)
     code = syms.astype(np.int32) & 0x1FF
-    out[off_cnt8:off_cnt8 + R] = np.minimum(counts, 255).astype(np.uint8)
+    nib = np.zeros((R + 1) // 2 * 2, dtype=np.uint8)
+    nib[:R] = np.minimum(counts.astype(np.int64) - 1, 15).astype(np.uint8)
+    out[off_cnt4:off_cnt4 + (R + 1) // 2] = nib[0::2] | (nib[1::2] << 4)
     out[off_sym8:off_sym8 + R] = (code & 0xFF).astype(np.uint8)
     bits = np.zeros((R + 31) // 32 * 32, dtype=np.uint8)
     bits[:R] = code >> 8

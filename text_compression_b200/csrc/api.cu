@@ -481,11 +481,11 @@ extern "C" int tc_bwt_mtf_rle_decode(tc_ctx *ctx, const uint32_t *count, const i
 static_assert(sizeof(tc_packed_header) == 640, "tc_packed_header layout");
 namespace {
 inline uint64_t al16(uint64_t x) { return (x + 15) & ~15ull; }
-inline uint64_t big_cap_for(uint64_t n) { return (n + 1) / 255 + 4; }
+inline uint64_t big_cap_for(uint64_t n) { return (n + 1) / 16 + 4; }
 // section offsets for R runs and n_big exceptions; returns the container size
 uint64_t packed_layout(uint64_t R, uint64_t n_big, tc_packed_header *h) {
     uint64_t o = sizeof(tc_packed_header);
-    h->off_cnt8 = o, o = al16(o + R);
+    h->off_cnt4 = o, o = al16(o + (R + 1) / 2);
     h->off_sym8 = o, o = al16(o + R);
     h->off_hi = o, o = al16(o + (R + 31) / 32 * 4);
     h->off_big_idx = o, o = al16(o + n_big * 8);
@@ -495,10 +495,10 @@ uint64_t packed_layout(uint64_t R, uint64_t n_big, tc_packed_header *h) {
 int packed_check(const void *blob, uint64_t bytes, tc_packed_header *h) {
     if (!blob || bytes < sizeof *h) return TC_E_ARG;
     memcpy(h, blob, sizeof *h);
-    if (h->magic != TC_PACKED_MAGIC || h->version != 1 || h->total_bytes > bytes || h->sigma > 257) return TC_E_ARG;
+    if (h->magic != TC_PACKED_MAGIC || h->version != 2 || h->total_bytes > bytes || h->sigma > 257) return TC_E_ARG;
     if (h->R > 0xffffffffull || h->n_big > h->R) return TC_E_ARG;
     tc_packed_header want;
-    if (packed_layout(h->R, h->n_big, &want) != h->total_bytes || want.off_cnt8 != h->off_cnt8 ||
+    if (packed_layout(h->R, h->n_big, &want) != h->total_bytes || want.off_cnt4 != h->off_cnt4 ||
         want.off_sym8 != h->off_sym8 || want.off_hi != h->off_hi || want.off_big_idx != h->off_big_idx ||
         want.off_big_cnt != h->off_big_cnt)
         return TC_E_ARG;
@@ -512,8 +512,10 @@ void packed_to_info(const tc_packed_header &h, tc_block_info *info) {
 } // namespace
 
 extern "C" uint64_t tc_packed_bound(uint64_t n) {
+    // R runs of total length n + 1 (+ the reference's extra pairs): every exception (count >= 16) costs 12 bytes but
+    // removes 15 runs of 1.625 bytes each, so the largest container is the one without exceptions
     tc_packed_header h;
-    return packed_layout(n + 3, big_cap_for(n), &h);
+    return packed_layout(n + 3, 4, &h);
 }
 
 extern "C" int tc_packed_info(const void *blob, uint64_t bytes, tc_block_info *info, uint32_t *flags) {
@@ -532,12 +534,12 @@ extern "C" int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *coun
     if (h.R > cap) return TC_E_CAP;
     if (h.R && (!count || !rsym)) return TC_E_ARG;
     const uint8_t *base = (const uint8_t *)blob;
-    const uint8_t *c8 = base + h.off_cnt8, *s8 = base + h.off_sym8;
+    const uint8_t *c4 = base + h.off_cnt4, *s8 = base + h.off_sym8;
     for (uint64_t k = 0; k < h.R; k++) {
         uint32_t w;
         memcpy(&w, base + h.off_hi + (k >> 5) * 4, 4);
         const uint32_t code = s8[k] | (((w >> (k & 31)) & 1u) << 8);
-        count[k] = c8[k];
+        count[k] = ((c4[k >> 1] >> (4 * (k & 1))) & 15u) + 1u;
         rsym[k] = code == 0x1ffu ? (int16_t)-1 : (int16_t)code;
     }
     uint64_t prev = 0;
@@ -546,7 +548,7 @@ extern "C" int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *coun
         uint32_t c;
         memcpy(&idx, base + h.off_big_idx + j * 8, 8);
         memcpy(&c, base + h.off_big_cnt + j * 4, 4);
-        if (idx >= h.R || (j && idx <= prev) || c < 255 || c8[idx] != 255) return TC_E_ARG;
+        if (idx >= h.R || (j && idx <= prev) || c < 16 || ((c4[idx >> 1] >> (4 * (idx & 1))) & 15u) != 15u) return TC_E_ARG;
         count[idx] = c;
         prev = idx;
     }
@@ -589,7 +591,7 @@ int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain
     int16_t *d_rsym = nullptr;
     for (int s = 0; s < 2; s++) {
         TC_TRY(ws_alloc(ctx, nmax ? nmax : 1, &d_text[s]));
-        TC_TRY(ws_alloc(ctx, al16(worst), &pk[s].cnt8));
+        TC_TRY(ws_alloc(ctx, al16(worst / 2 + 16), &pk[s].cnt4));
         TC_TRY(ws_alloc(ctx, al16(worst), &pk[s].sym8));
         TC_TRY(ws_alloc(ctx, (worst + 31) / 32, &pk[s].hi));
         pk[s].big_cap = big_cap_for(nmax);
@@ -627,7 +629,7 @@ int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         tc_packed_header h;
         memset(&h, 0, sizeof h);
-        h.magic = TC_PACKED_MAGIC, h.version = 1, h.flags = with_mtf ? TC_PACKED_MTF : 0;
+        h.magic = TC_PACKED_MAGIC, h.version = 2, h.flags = with_mtf ? TC_PACKED_MTF : 0;
         h.n = info[b].n, h.N = info[b].N, h.primary = info[b].primary, h.R = info[b].R, h.sigma = info[b].sigma;
         h.n_big = n[b] ? pk[s].n_big : 0;
         memcpy(h.final_list, info[b].final_list, sizeof h.final_list);
@@ -645,7 +647,7 @@ int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain
             memset(o + off + len, 0, next - off - len);
             return TC_OK;
         };
-        TC_TRY(section(h.off_cnt8, pk[s].cnt8, h.R, h.off_sym8));
+        TC_TRY(section(h.off_cnt4, pk[s].cnt4, (h.R + 1) / 2, h.off_sym8));
         TC_TRY(section(h.off_sym8, pk[s].sym8, h.R, h.off_hi));
         TC_TRY(section(h.off_hi, pk[s].hi, (h.R + 31) / 32 * 4, h.off_big_idx));
         TC_TRY(section(h.off_big_idx, pk[s].big_idx, h.n_big * 8, h.off_big_cnt));
@@ -764,12 +766,12 @@ extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, u
     uint8_t *d_blob; // payload sections keep their 16-byte alignment on the device
     uint32_t *d_count;
     int16_t *d_rsym;
-    const uint64_t pay = h.total_bytes - h.off_cnt8;
+    const uint64_t pay = h.total_bytes - h.off_cnt4;
     TC_TRY(ws_alloc(ctx, pay, &d_blob));
     TC_TRY(ws_alloc(ctx, h.R, &d_count));
     TC_TRY(ws_alloc(ctx, h.R, &d_rsym));
-    TC_TRY(h2d(ctx, d_blob, base + h.off_cnt8, pay));
-    const uint64_t o0 = h.off_cnt8;
+    TC_TRY(h2d(ctx, d_blob, base + h.off_cnt4, pay));
+    const uint64_t o0 = h.off_cnt4;
     TC_TRY(rle_unpack_dev_impl(ctx, d_blob, d_blob + (h.off_sym8 - o0), (const uint32_t *)(d_blob + (h.off_hi - o0)),
                                (const uint64_t *)(d_blob + (h.off_big_idx - o0)),
                                (const uint32_t *)(d_blob + (h.off_big_cnt - o0)), h.n_big, h.R, d_count, d_rsym));

@@ -31,9 +31,9 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
 // Packed form of the runs (payload of the block container; layout in rle.cu).
 // All pointers are device pointers sized for `cap` runs; n_big comes back on the host.
 struct RlePack {
-    uint8_t *cnt8 = nullptr, *sym8 = nullptr; // [cap rounded up to 8]
+    uint8_t *cnt4 = nullptr, *sym8 = nullptr; // [cap / 2 rounded up to 16], [cap rounded up to 16]
     uint32_t *hi = nullptr;                   // [ceil(cap / 32)]
-    uint64_t *big_idx = nullptr;              // [big_cap] runs with count >= 255, sorted by run index
+    uint64_t *big_idx = nullptr;              // [big_cap] runs with count >= 16, sorted by run index
     uint32_t *big_cnt = nullptr;
     uint64_t big_cap = 0;
     uint64_t n_big = 0;
@@ -42,7 +42,7 @@ int rle_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64
                            int16_t *d_rsym, uint64_t cap, uint64_t *R, RlePack *pk = nullptr);
 int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint32_t *d_count, int16_t *d_rsym,
                             uint64_t cap, uint64_t *R, RlePack *pk = nullptr, const MtfRleLink *link = nullptr);
-int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt8, const uint8_t *d_sym8, const uint32_t *d_hi,
+int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt4, const uint8_t *d_sym8, const uint32_t *d_hi,
                         const uint64_t *d_big_idx, const uint32_t *d_big_cnt, uint64_t n_big, uint64_t R,
                         uint32_t *d_count, int16_t *d_rsym);
 int rle_encode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_sym, uint64_t N, uint32_t *d_count, int16_t *d_rsym,

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(1024)
 }
 
 struct PackArgs { // device pointers of RlePack, passed by value to the emit kernel
-    uint8_t *cnt8, *sym8;
+    uint8_t *cnt4, *sym8;
     uint32_t *hi;
     uint64_t *big_idx;
     uint32_t *big_cnt;
@@ -230,10 +230,10 @@ __device__ __forceinline__ void rle_emit_tile(In in, uint64_t N, uint64_t lim_en
     auto put = [&](uint32_t slot, uint32_t cnt, int sym) {
         if (PACKED) {
             const uint32_t j = padp + slot;
-            s_c8[j] = (uint8_t)min(cnt, 255u);
+            s_c8[j] = (uint8_t)min(cnt - 1u, 15u); // count - 1 in four bits; 15 = see the exception list
             s_s8[j] = (uint8_t)sym;
             if (sym & 0x100) atomicOr(&s_hi[j >> 5], 1u << (j & 31)); // MTF index 256, Nothing (-1)
-            if (cnt >= 255u) {
+            if (cnt >= 16u) {
                 const unsigned long long e = atomicAdd(pk.n_big, 1ull);
                 if (e < pk.big_cap) {
                     pk.big_idx[e] = goff + slot;
@@ -338,14 +338,36 @@ __device__ __forceinline__ void rle_emit_tile(In in, uint64_t N, uint64_t lim_en
             for (uint32_t v = threadIdx.x; v < nv; v += RT) {
                 const uint32_t j0 = 16 * v;
                 if (j0 >= padp && j0 + 16 <= padp + tile_total) {
-                    *reinterpret_cast<uint4 *>(pk.cnt8 + gp + j0) = *reinterpret_cast<const uint4 *>(s_c8 + j0);
                     *reinterpret_cast<uint4 *>(pk.sym8 + gp + j0) = *reinterpret_cast<const uint4 *>(s_s8 + j0);
                 } else {
                     for (uint32_t j = j0; j < j0 + 16; j++)
-                        if (j >= padp && j < padp + tile_total) {
-                            pk.cnt8[gp + j] = s_c8[j];
-                            pk.sym8[gp + j] = s_s8[j];
-                        }
+                        if (j >= padp && j < padp + tile_total) pk.sym8[gp + j] = s_s8[j];
+                }
+            }
+            // counts: two per byte (run k in the low nibble of byte k / 2 when k is even), 32 runs = 16 bytes per
+            // store; a 16-byte group shared with a neighbouring tile is OR-ed into the (zeroed) plane byte by byte
+            const uint32_t nq = (padp + tile_total + 31) / 32;
+            for (uint32_t v = threadIdx.x; v < nq; v += RT) {
+                const uint32_t j0 = 32 * v;
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const uint32_t j = j0 + 8 * q + e;
+                        const uint32_t c = (j >= padp && j < padp + tile_total) ? s_c8[j] : 0u;
+                        x |= c << (4 * e);
+                    }
+                    w[q] = x;
+                }
+                uint8_t *dst = pk.cnt4 + ((gp + j0) >> 1);
+                if (j0 >= padp && j0 + 32 <= padp + tile_total) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (w[q]) atomicOr(reinterpret_cast<uint32_t *>(dst) + q, w[q]);
                 }
             }
             // hi plane in whole words; a word shared with a neighbouring tile is OR-ed into the
@@ -479,22 +501,22 @@ __global__ void __launch_bounds__(RT)
 
 // ---- packed run payload (block container) ------------------------------------
 // Runs leave the device as 2 bytes + 1 bit each instead of the 6-byte record:
-//   cnt8[k] = min(count, 255); sym8[k] = low byte of the symbol; hi bit k = bit 8 of the
+//   cnt4: min(count - 1, 15) in four bits per run; sym8[k] = low byte of the symbol; hi bit k = bit 8 of the
 //   symbol's 9-bit code (set for MTF index 256 and for Nothing, whose code is 0x1ff);
-//   counts >= 255 are listed as (run index, count) exceptions, appended in arbitrary order by
+//   counts >= 16 are listed as (run index, count) exceptions, appended in arbitrary order by
 //   the emit kernel and sorted by run index before they leave the device.
 // rle_emit_kernel<In, true> stages this form in shared memory and writes it straight out (the
 // 6-byte records are never written): byte streams in aligned groups of 16 runs, the hi plane in
 // whole 32-run words, with atomicOr on the (zeroed) words a tile shares with its neighbours.
 
 // inverse of the packing for the device-side decoder: one thread per run; exceptions patched after
-__global__ void rle_unpack_kernel(const uint8_t *__restrict__ cnt8, const uint8_t *__restrict__ sym8,
+__global__ void rle_unpack_kernel(const uint8_t *__restrict__ cnt4, const uint8_t *__restrict__ sym8,
                                   const uint32_t *__restrict__ hi, uint64_t R, uint32_t *__restrict__ count,
                                   int16_t *__restrict__ rsym) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= R) return;
     const uint32_t code = sym8[k] | (((hi[k >> 5] >> (k & 31)) & 1u) << 8);
-    count[k] = cnt8[k];
+    count[k] = ((cnt4[k >> 1] >> (4 * (k & 1))) & 15u) + 1u;
     rsym[k] = code == 0x1ffu ? (int16_t)-1 : (int16_t)code;
 }
 __global__ void rle_unpack_big_kernel(const uint64_t *__restrict__ big_idx, const uint32_t *__restrict__ big_cnt,
@@ -552,7 +574,8 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
         pk->n_big = 0;
         TC_CUDA(cudaMemsetAsync(d_R + 1, 0, sizeof(uint64_t), ctx->stream));
         TC_CUDA(cudaMemsetAsync(pk->hi, 0, ceil_div_u64(cap, 32) * sizeof(uint32_t), ctx->stream));
-        pa = PackArgs{pk->cnt8, pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap, (unsigned long long *)(d_R + 1)};
+        TC_CUDA(cudaMemsetAsync(pk->cnt4, 0, ceil_div_u64(cap, 32) * 16, ctx->stream));
+        pa = PackArgs{pk->cnt4, pk->sym8, pk->hi, pk->big_idx, pk->big_cnt, pk->big_cap, (unsigned long long *)(d_R + 1)};
     }
     ctx->prof_bytes_next = N * sizeof(*in.p);
     if (tiled) {
@@ -669,11 +692,11 @@ int rle_encode_u16_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, uint
                             uint64_t cap, uint64_t *R, RlePack *pk, const MtfRleLink *link) {
     return rle_encode_impl(ctx, In16<false>{d_idx}, N, d_count, d_rsym, cap, R, pk, link);
 }
-int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt8, const uint8_t *d_sym8, const uint32_t *d_hi,
+int rle_unpack_dev_impl(tc_ctx *ctx, const uint8_t *d_cnt4, const uint8_t *d_sym8, const uint32_t *d_hi,
                         const uint64_t *d_big_idx, const uint32_t *d_big_cnt, uint64_t n_big, uint64_t R,
                         uint32_t *d_count, int16_t *d_rsym) {
     if (R == 0) return TC_OK;
-    TC_LAUNCH(ctx, rle_unpack_kernel, (unsigned)ceil_div_u64(R, 256), 256, 0, d_cnt8, d_sym8, d_hi, R, d_count, d_rsym);
+    TC_LAUNCH(ctx, rle_unpack_kernel, (unsigned)ceil_div_u64(R, 256), 256, 0, d_cnt4, d_sym8, d_hi, R, d_count, d_rsym);
     if (n_big)
         TC_LAUNCH(ctx, rle_unpack_big_kernel, (unsigned)ceil_div_u64(n_big, 256), 256, 0, d_big_idx, d_big_cnt, n_big, R,
                   d_count);

@@ -539,49 +539,50 @@ struct FsWarp {
 };
 enum { FL_TIES = 0, FL_OVERFLOW = 1 };
 
-// ascending sort of 32*PER words, element index = lane * PER + r.  "Flip" form of the bitonic
-// network: the first step of every merge pairs e with e ^ (k-1), the others e with e ^ j, and
-// every compare-exchange leaves the minimum at the lower index -- no direction flags.
-template <int PER>
+// Ascending sort of 32 * PER words held as v[r] of lane l = element r * 32 + l, by the bitonic network of
+// 32 * REG >= 32 * PER elements whose upper REG - PER registers are +infinity and therefore never materialise: a
+// compare-exchange leaves the minimum at the lower index, so one whose upper side is +infinity changes nothing
+// and is skipped at compile time.  Buckets hold 256 records on average, so half of them are a little larger than
+// 256: they are sorted as 320 or 384 elements instead of 512.  "Flip" form of the network: the first step of
+// every merge pairs e with e ^ (k-1), the others e with e ^ j -- no direction flags.  Strides below 32 are
+// shuffles, strides of 32 and more stay inside the lane.
+template <int PER, int REG>
 __device__ __forceinline__ void warp_bitonic(uint32_t (&v)[PER], unsigned lane) {
 #pragma unroll
-    for (int k = 2; k <= 32 * PER; k <<= 1) {
-        // flip step: partner = e ^ (k - 1)
-        if (k <= PER) {
+    for (int k = 2; k <= 32 * REG; k <<= 1) {
+        if (k <= 32) { // flip inside the lanes' dimension: partner lane = lane ^ (k - 1), same register
+            const bool lower = (lane & (k >> 1)) == 0;
 #pragma unroll
             for (int r = 0; r < PER; r++) {
-                const int p = r ^ (k - 1);
-                if (p > r) {
-                    uint32_t a = min(v[r], v[p]), c = max(v[r], v[p]);
-                    v[r] = a;
-                    v[p] = c;
+                const uint32_t o = __shfl_xor_sync(TC_FULL, v[r], k - 1);
+                v[r] = lower ? min(v[r], o) : max(v[r], o);
+            }
+        } else { // partner = (r ^ (k/32 - 1), lane ^ 31)
+#pragma unroll
+            for (int r = 0; r < PER; r++) {
+                const int p = r ^ (k / 32 - 1);
+                if (p > r && p < PER) {
+                    const uint32_t op = __shfl_xor_sync(TC_FULL, v[p], 31), orr = __shfl_xor_sync(TC_FULL, v[r], 31);
+                    v[r] = min(v[r], op);
+                    v[p] = max(v[p], orr);
                 }
             }
-        } else {
-            const int lx = k / PER - 1;                       // partner lane = lane ^ lx, partner r = PER-1-r
-            const bool lower = (lane & (k / PER / 2)) == 0;
-            uint32_t o[PER];
-#pragma unroll
-            for (int r = 0; r < PER; r++) o[r] = __shfl_xor_sync(TC_FULL, v[PER - 1 - r], lx);
-#pragma unroll
-            for (int r = 0; r < PER; r++) v[r] = lower ? min(v[r], o[r]) : max(v[r], o[r]);
         }
 #pragma unroll
         for (int j = k >> 2; j > 0; j >>= 1) {
-            if (j >= PER) {
-                const int lx = j / PER;
-                const bool lower = (lane & lx) == 0;
+            if (j < 32) {
+                const bool lower = (lane & j) == 0;
 #pragma unroll
                 for (int r = 0; r < PER; r++) {
-                    uint32_t o = __shfl_xor_sync(TC_FULL, v[r], lx);
+                    const uint32_t o = __shfl_xor_sync(TC_FULL, v[r], j);
                     v[r] = lower ? min(v[r], o) : max(v[r], o);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < PER; r++) {
-                    const int p = r ^ j;
-                    if (p > r) {
-                        uint32_t a = min(v[r], v[p]), c = max(v[r], v[p]);
+                    const int p = r ^ (j / 32);
+                    if (p > r && p < PER) {
+                        const uint32_t a = min(v[r], v[p]), c = max(v[r], v[p]);
                         v[r] = a;
                         v[p] = c;
                     }
@@ -592,7 +593,7 @@ __device__ __forceinline__ void warp_bitonic(uint32_t (&v)[PER], unsigned lane) 
 }
 
 // load the bucket (coalesced), sort it, leave the sorted words in we[0..M)
-template <int PER>
+template <int PER, int REG>
 __device__ __forceinline__ bool fs_sort_bucket(const uint2 *__restrict__ rec, uint32_t M, int fsh, uint32_t fmask,
                                                uint32_t *we, unsigned lane) {
     uint32_t v[PER];
@@ -601,16 +602,17 @@ __device__ __forceinline__ bool fs_sort_bucket(const uint2 *__restrict__ rec, ui
         uint32_t j = lane + 32 * r; // any assignment of records to registers will do
         v[r] = j < M ? ((((rec[j].x >> fsh) & fmask) << 9) | j) : 0xffffffffu;
     }
-    warp_bitonic<PER>(v, lane);
+    warp_bitonic<PER, REG>(v, lane);
     // neighbours with equal field?  (padding words are all ones and never tie with a record)
     bool tie = false;
 #pragma unroll
-    for (int r = 0; r + 1 < PER; r++) tie |= (v[r] >> 9) == (v[r + 1] >> 9) && lane * PER + r + 1 < M;
-    const uint32_t nxt = __shfl_down_sync(TC_FULL, v[0], 1);
-    tie |= lane < 31 && (v[PER - 1] >> 9) == (nxt >> 9) && (lane + 1) * PER < M;
-#pragma unroll
-    for (int r = 0; r < PER; r++)
-        if (lane * PER + r < M) we[lane * PER + r] = v[r];
+    for (int r = 0; r < PER; r++) {
+        const uint32_t nx = __shfl_down_sync(TC_FULL, v[r], 1);
+        const uint32_t n0 = r + 1 < PER ? __shfl_sync(TC_FULL, v[r + 1 < PER ? r + 1 : r], 0) : 0xffffffffu;
+        const uint32_t next = lane == 31 ? n0 : nx;
+        tie |= (v[r] >> 9) == (next >> 9) && r * 32 + lane + 1 < M;
+        if (r * 32 + lane < M) we[r * 32 + lane] = v[r];
+    }
     __syncwarp();
     return __any_sync(TC_FULL, tie);
 }
@@ -687,8 +689,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 5)
     const int fbits = rb < 23 ? rb : 23;
     const int fsh = rb - fbits;
     const uint32_t fmask = (fbits ? (0xffffffffu >> (32 - fbits)) : 0u);
-    const bool any_tie = M <= 256 ? fs_sort_bucket<8>(rec + s, M, fsh, fmask, W.e, lane)
-                                  : fs_sort_bucket<16>(rec + s, M, fsh, fmask, W.e, lane);
+    const bool any_tie = M <= 256   ? fs_sort_bucket<8, 8>(rec + s, M, fsh, fmask, W.e, lane)
+                         : M <= 320 ? fs_sort_bucket<10, 16>(rec + s, M, fsh, fmask, W.e, lane)
+                         : M <= 384 ? fs_sort_bucket<12, 16>(rec + s, M, fsh, fmask, W.e, lane)
+                                    : fs_sort_bucket<16, 16>(rec + s, M, fsh, fmask, W.e, lane);
     // runs of equal field (rare): the lane holding the head of a run sorts it by full keys
     bool head = false;
     uint32_t eqpairs = 0;
