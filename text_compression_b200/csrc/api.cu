@@ -279,6 +279,9 @@ int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, 
     for (int c = 0; c < 256; c++) present[c + 1] = ctx->text_hist[c] != 0;
     MtfRleLink link; // the MTF replay counts the runs of its tiles while the indices are in registers
     TC_TRY(ws_alloc(ctx, ceil_div_u64(N, 4096) + 1, &link.d_tstat));
+    TC_TRY(ws_alloc(ctx, ceil_div_u64(N, 4096) + 1, &link.d_toff));
+    TC_TRY(ws_alloc(ctx, ceil_div_u64(N, 4096) + 1, &link.d_theadx));
+    TC_TRY(ws_alloc(ctx, 2, &link.d_ticket));
     TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma, present, &link));
     int rc = rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R, pk, &link); // syncs the stream
     int rc2 = mtf_finish_pending(ctx);

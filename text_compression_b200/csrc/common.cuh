@@ -242,4 +242,67 @@ __device__ __forceinline__ T block_excl_max(T v, T ident, T *sh, T *total) {
     __syncthreads();
     return r;
 }
+// Run statistics of an MTF index stream (mtf.cu RunStat -> rle.cu rle_emit_tiled_kernel): tstat[T] = (run boundaries
+// inside MTF tile T, 1 + position of the last one, first index, last index).  One CTA of THREADS threads: the
+// boundary at the start of every tile is decided here (first index against the last index of the tile before),
+// then exclusive sum of the runs and exclusive max of the heads over the tiles.  Called by the last CTA of the
+// replay kernel (loads bypass L1: other SMs wrote the records), or as a kernel of its own.
+template <int THREADS>
+__device__ __noinline__ void runstat_scan(const uint4 *__restrict__ tstat, uint64_t ntiles, uint32_t tile_syms,
+                                             uint64_t *__restrict__ toff, uint32_t *__restrict__ theadx) {
+    constexpr int PER = 12; // records per thread and round: 16 MiB blocks (1,366 or 4,097 tiles) take one or two rounds
+    __shared__ uint64_t rs_sh64[THREADS / 32 + 1];
+    __shared__ uint32_t rs_sh32[THREADS / 32 + 1];
+    uint64_t carry = 0;
+    uint32_t ch = 0;
+    for (uint64_t b = 0; b < ntiles; b += (uint64_t)THREADS * PER) {
+        const uint64_t t0 = b + (uint64_t)threadIdx.x * PER;
+        uint4 me[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) me[q] = t0 + q < ntiles ? __ldcg(&tstat[t0 + q]) : make_uint4(0, 0, 0, 0);
+        uint32_t before = t0 > 0 && t0 - 1 < ntiles ? __ldcg(&tstat[t0 - 1]).w : 0u;
+        uint64_t v = 0;
+        uint32_t hm = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const uint64_t t = t0 + q;
+            uint32_t p = 0, h = 0;
+            if (t < ntiles) {
+                const bool starts = t == 0 || me[q].z != before; // a run starts at the tile's first position
+                p = me[q].x + (t > 0 && starts);
+                h = max(me[q].y, starts ? (uint32_t)(t * tile_syms) + 1u : 0u);
+                before = me[q].w;
+            }
+            me[q].x = p, me[q].y = h;
+            v += p;
+            hm = max(hm, h);
+        }
+        uint64_t tot;
+        uint32_t th;
+        uint64_t ex = carry + block_excl_sum<uint64_t, THREADS>(v, rs_sh64, &tot);
+        uint32_t hx = max(ch, block_excl_max<uint32_t, THREADS>(hm, 0u, rs_sh32, &th));
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (t0 + q < ntiles) {
+                toff[t0 + q] = ex;
+                theadx[t0 + q] = hx;
+            }
+            ex += me[q].x;
+            hx = max(hx, me[q].y);
+        }
+        carry += tot;
+        ch = max(ch, th);
+    }
+}
+// last-CTA election for kernels that finish with a small serial step: every thread of every CTA calls it after its
+// global writes; true in exactly one CTA, and only after all the others' writes are visible
+__device__ __forceinline__ bool last_cta_done(uint32_t *ticket, uint32_t nctas) {
+    __shared__ uint32_t lc_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) lc_last = atomicAdd(ticket, 1u) == nctas - 1;
+    __syncthreads();
+    if (lc_last) __threadfence();
+    return lc_last != 0;
+}
 #endif

@@ -15,6 +15,10 @@ int bwt_decode_i16_dev_impl(tc_ctx *ctx, const int16_t *d_bwt, uint64_t N, uint8
 // stage needs no counting pass over the index stream (rle.cu rle_emit_tiled_kernel).
 struct MtfRleLink {
     uint4 *d_tstat = nullptr; // caller-allocated: ceil(N / 4096) records (a tile has at least 4096 symbols)
+    uint64_t *d_toff = nullptr;    // caller-allocated, same count: runs before each tile ...
+    uint32_t *d_theadx = nullptr;  // ... and the latest run head before it, both written by the replay kernel's last CTA
+    uint32_t *d_ticket = nullptr;  // caller-allocated, 2 words (zeroed by the first MTF kernel)
+    bool scanned = false;     // d_toff / d_theadx are filled
     uint64_t ntiles = 0;      // set by the MTF stage
     uint32_t tile_syms = 0;   // symbols per tile
     bool valid = false;       // false: the MTF path taken does not collect them

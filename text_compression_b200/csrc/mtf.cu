@@ -570,9 +570,9 @@ constexpr int T1_WARPS = 1; // one tile per CTA: 1,366 tiles of a 16 MiB block s
 template <class Src>
 __global__ void __launch_bounds__(T1_WARPS * 32)
     mtf3_tile_last_kernel(Src src, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t *__restrict__ trow,
-                          uint16_t *__restrict__ start, uint32_t *__restrict__ scan_ticket) {
+                          uint16_t *__restrict__ start, uint32_t *__restrict__ scan_ticket, uint32_t *__restrict__ rle_ticket) {
     extern __shared__ __align__(16) uint32_t smt1[];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *scan_ticket = 0; // for T2's "last CTA" election
+    if (blockIdx.x == 0 && threadIdx.x == 0) scan_ticket[0] = 0, rle_ticket[0] = 0; // the "last CTA" elections of T2 and of the replay
     const unsigned lane = lane_id();
     const uint64_t tile = (uint64_t)blockIdx.x * T1_WARPS + (threadIdx.x >> 5);
     if (tile * TT_CH >= nchunks) return;
@@ -850,7 +850,8 @@ __device__ __forceinline__ uint32_t r3_step(R3 &S, const uint64_t *m8tab, uint32
 template <class Src, int CT, bool RS>
 __global__ void __launch_bounds__(CT)
     mtf3_replay_kernel(Src src, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t sigma,
-                       const uint16_t *__restrict__ start, uint16_t *__restrict__ idx_out, uint4 *__restrict__ tstat) {
+                       const uint16_t *__restrict__ start, uint16_t *__restrict__ idx_out, uint4 *__restrict__ tstat,
+                       uint64_t *__restrict__ toff, uint32_t *__restrict__ theadx, uint32_t *__restrict__ ticket) {
     extern __shared__ __align__(16) uint32_t sm3[];
     __shared__ uint64_t m8tab[8];
     if (threadIdx.x < 8) m8tab[threadIdx.x] = 0x0001010101010101ull >> (56u - 8u * threadIdx.x); // bytes below kk
@@ -971,7 +972,11 @@ __global__ void __launch_bounds__(CT)
         j = (j + 1) & 31u;
     }
     } // active
-    if (RS) rs.finish(active, (uint32_t)(k * L), k >> 5, tstat);
+    if (RS) {
+        rs.finish(active, (uint32_t)(k * L), k >> 5, tstat);
+        // the CTA that finishes last scans the tile records for the RLE stage (no kernel of its own for that)
+        if (last_cta_done(ticket, gridDim.x)) runstat_scan<CT>(tstat, (nchunks + 31) / 32, 32 * L, toff, theadx);
+    }
 }
 
 // ---- encode, small alphabets (sigma <= 8: ACGT(N) + sentinel) -------------------------------------
@@ -1226,10 +1231,11 @@ template <class Src>
 __global__ void __launch_bounds__(AU_T, 4)
     mtfa_summary_kernel(Src src, AutoHash hs, uint64_t N, const uint16_t *__restrict__ g_perm,
                         const uint32_t *__restrict__ g_list, uint32_t n_perm, Summ *__restrict__ part,
-                        Summ *__restrict__ tot) {
+                        Summ *__restrict__ tot, uint32_t *__restrict__ rle_ticket) {
     extern __shared__ __align__(16) uint32_t sma[];
     AutoSmem &A = *reinterpret_cast<AutoSmem *>(sma);
     __shared__ Summ wsum[AU_T / 32];
+    if (rle_ticket && blockIdx.x == 0 && threadIdx.x == 0) *rle_ticket = 0; // the replay kernel's last-CTA election
     auto_load_tables(A, g_perm, g_list, n_perm);
     __syncthreads();
     const uint64_t chunk = (uint64_t)blockIdx.x * AU_T + threadIdx.x;
@@ -1297,7 +1303,8 @@ __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 
     mtfa_replay_kernel(Src src, AutoHash hs, uint64_t N, const uint16_t *__restrict__ g_perm,
                        const uint32_t *__restrict__ g_list, uint32_t n_perm, const Summ *__restrict__ part,
                        const uint32_t *__restrict__ start_list, uint32_t sigma, uint16_t *__restrict__ idx_out,
-                       uint4 *__restrict__ tstat) {
+                       uint4 *__restrict__ tstat, uint64_t *__restrict__ toff, uint32_t *__restrict__ theadx,
+                       uint32_t *__restrict__ ticket) {
     extern __shared__ __align__(16) uint32_t sma[];
     AutoSmem &A = *reinterpret_cast<AutoSmem *>(sma);
     auto_load_tables(A, g_perm, g_list, n_perm);
@@ -1305,12 +1312,13 @@ __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 
     const uint64_t chunk = (uint64_t)blockIdx.x * AU_T + threadIdx.x;
     const uint64_t base = chunk * AU_L;
     const uint64_t wbase = (chunk & ~31ull) * AU_L;
-    if (wbase >= N) return;
+    if (!RS && wbase >= N) return;
+    RunStat rs;
+    if (wbase < N) { // (with RS every thread reaches the election at the end)
     const char *tab = reinterpret_cast<const char *>(A.perm);
     const uint32_t full = (1u << sigma) - 1u;
     uint32_t st = 0;
     if (base < N) st = perm_rank(summ_compose(Summ{start_list[blockIdx.x], full}, part[chunk]).list, sigma) * (2 * AU_RW);
-    RunStat rs;
     bool done = false;
     if constexpr (sizeof(*src.p) == 1) {
         if (wbase + 32 * AU_L <= N && src.can_vec(wbase) && (reinterpret_cast<uintptr_t>(idx_out + wbase) & 15) == 0) {
@@ -1364,7 +1372,11 @@ __global__ void __launch_bounds__(AU_T, 4) // 4 CTAs per SM: the 512 tiles of a 
             if (RS) rs.see(e & 7u, (uint32_t)pos);
         }
     }
-    if (RS) rs.finish(base < N, (uint32_t)base, chunk >> 5, tstat);
+    } // wbase < N
+    if (RS) {
+        rs.finish(base < N, (uint32_t)base, chunk >> 5, tstat);
+        if (last_cta_done(ticket, gridDim.x)) runstat_scan<AU_T>(tstat, (N + 32 * AU_L - 1) / (32 * AU_L), 32 * AU_L, toff, theadx);
+    }
 }
 
 // ---- decode ----------------------------------------------------------------------------------
@@ -1726,7 +1738,7 @@ template <class Src>
 int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *final_list, uint32_t *sigma_out,
                     const uint8_t *present_hint = nullptr, MtfRleLink *link = nullptr) {
     *sigma_out = 0;
-    if (link) link->valid = false;
+    if (link) link->valid = link->scanned = false;
     if (N == 0) return TC_OK;
     if (N >= 0x7fffffffull) return TC_E_TOOBIG; // recency keys are 32-bit distances (see list_positions)
     WsMark mk = tc_ws_mark(ctx);
@@ -1779,16 +1791,17 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         }
         ctx->prof_bytes_next = N * sizeof(*src.p);
         TC_LAUNCH(ctx, (mtfa_summary_kernel<Src>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list, at.n_perm,
-                  part, tot);
+                  part, tot, link ? link->d_ticket : (uint32_t *)nullptr);
         TC_LAUNCH(ctx, mtfs_top_kernel, 1, 1024, 0, tot, ntiles, sigma, start_list, d_final);
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
         if (link) {
             TC_LAUNCH(ctx, (mtfa_replay_kernel<Src, true>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list,
-                      at.n_perm, part, start_list, sigma, d_idx, link->d_tstat);
-            link->ntiles = ceil_div_u64(N, 32 * AU_L), link->tile_syms = 32 * AU_L, link->valid = true;
+                      at.n_perm, part, start_list, sigma, d_idx, link->d_tstat, link->d_toff, link->d_theadx, link->d_ticket);
+            link->ntiles = ceil_div_u64(N, 32 * AU_L), link->tile_syms = 32 * AU_L, link->valid = true, link->scanned = true;
         } else {
             TC_LAUNCH(ctx, (mtfa_replay_kernel<Src, false>), (unsigned)ntiles, AU_T, sma, src, at.hash, N, at.d_perm, at.d_list,
-                      at.n_perm, part, start_list, sigma, d_idx, (uint4 *)nullptr);
+                      at.n_perm, part, start_list, sigma, d_idx, (uint4 *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                      (uint32_t *)nullptr);
         }
         *sigma_out = sigma;
         int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
@@ -1825,7 +1838,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         uint32_t *trow, *finalocc;
         uint16_t *d_final, *start;
         TC_TRY(ws_alloc(ctx, ntiles * R3_ROW, &trow));
-        TC_TRY(ws_alloc(ctx, R3_ROW + 32, &finalocc)); // + the ticket of the scan kernel's last-CTA election
+        TC_TRY(ws_alloc(ctx, R3_ROW + 32, &finalocc)); // + the tickets of the last-CTA elections
         uint32_t *segpre;
         TC_TRY(ws_alloc(ctx, (size_t)T2_SEGS * R3_ROW, &segpre));
         const uint32_t seg_tiles = (uint32_t)std::max<uint64_t>(1, ceil_div_u64(ntiles, T2_SEGS));
@@ -1852,7 +1865,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
             ctx->attr_done |= abit;
         }
         TC_LAUNCH(ctx, (mtf3_tile_last_kernel<Src>), (unsigned)ceil_div_u64(ntiles, T1_WARPS), T1_WARPS * 32, smem1, src, N,
-                  L, nchunks, trow, start, ticket);
+                  L, nchunks, trow, start, ticket, link ? link->d_ticket : ticket + 1);
         TC_LAUNCH(ctx, mtf3_tile_scan_kernel, dim3(R3_ROW / 32, T2_SEGS), T2_WARPS * 32, 0, trow, ntiles, seg_tiles, segpre,
                   finalocc, ticket);
         TC_LAUNCH(ctx, mtf3_starts_kernel, (unsigned)ceil_div_u64(ntiles, T3_WARPS) + 1, T3_WARPS * 32, 0, pr, sigma, L,
@@ -1860,11 +1873,12 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
         if (link) {
             TC_LAUNCH(ctx, (mtf3_replay_kernel<Src, R3_CT, true>), (unsigned)ceil_div_u64(nchunks, R3_CT), R3_CT, smem3, src, N, L,
-                      nchunks, sigma, start, d_idx, link->d_tstat);
-            link->ntiles = ceil_div_u64(nchunks, 32), link->tile_syms = 32 * L, link->valid = true;
+                      nchunks, sigma, start, d_idx, link->d_tstat, link->d_toff, link->d_theadx, link->d_ticket);
+            link->ntiles = ceil_div_u64(nchunks, 32), link->tile_syms = 32 * L, link->valid = true, link->scanned = true;
         } else {
             TC_LAUNCH(ctx, (mtf3_replay_kernel<Src, R3_CT, false>), (unsigned)ceil_div_u64(nchunks, R3_CT), R3_CT, smem3, src, N,
-                      L, nchunks, sigma, start, d_idx, (uint4 *)nullptr);
+                      L, nchunks, sigma, start, d_idx, (uint4 *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                      (uint32_t *)nullptr);
         }
         *sigma_out = sigma;
         int rc = mtf_read_final(ctx, d_final, sigma, alpha_li, final_list, present_hint != nullptr, SIGMAX);

@@ -431,50 +431,12 @@ __global__ void __launch_bounds__(RT)
 }
 
 // ---- runs of an MTF index stream whose statistics the MTF replay kernel collected (mtf.cu RunStat) --------------
-// tstat[T] = (run boundaries inside MTF tile T, 1 + position of the last one, first index, last index).  One CTA:
-// the boundary at the start of every tile is decided here (first index against the last index of the tile before),
-// then exclusive sum of the runs and exclusive max of the heads over the tiles.
+// The scan over the tile records (common.cuh runstat_scan) normally runs in the last CTA of the replay kernel; this
+// kernel is the stand-alone form.
 __global__ void __launch_bounds__(1024)
     rle_tstat_scan_kernel(const uint4 *__restrict__ tstat, uint64_t ntiles, uint32_t tile_syms, uint64_t *__restrict__ toff,
                           uint32_t *__restrict__ theadx) {
-    __shared__ uint64_t sh64[1024 / 32 + 1];
-    __shared__ uint32_t sh32[1024 / 32 + 1];
-    uint64_t carry = 0;
-    uint32_t ch = 0;
-    for (uint64_t b = 0; b < ntiles; b += 1024 * 4) {
-        const uint64_t t0 = b + (uint64_t)threadIdx.x * 4;
-        uint32_t p[4], h[4];
-        uint64_t v = 0;
-        uint32_t hm = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint64_t t = t0 + q;
-            p[q] = h[q] = 0;
-            if (t < ntiles) {
-                const uint4 me = tstat[t];
-                const bool starts = t == 0 || me.z != tstat[t - 1].w; // a run starts at the tile's first position
-                p[q] = me.x + (t > 0 && starts);
-                h[q] = max(me.y, starts ? (uint32_t)(t * tile_syms) + 1u : 0u);
-            }
-            v += p[q];
-            hm = max(hm, h[q]);
-        }
-        uint64_t tot;
-        uint32_t th;
-        uint64_t ex = carry + block_excl_sum<uint64_t, 1024>(v, sh64, &tot);
-        uint32_t hx = max(ch, block_excl_max<uint32_t, 1024>(hm, 0u, sh32, &th));
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (t0 + q < ntiles) {
-                toff[t0 + q] = ex;
-                theadx[t0 + q] = hx;
-            }
-            ex += p[q];
-            hx = max(hx, h[q]);
-        }
-        carry += tot;
-        ch = max(ch, th);
-    }
+    runstat_scan<1024>(tstat, ntiles, tile_syms, toff, theadx);
 }
 
 // CTA per MTF tile: its tile_syms positions in sub-tiles of RT * ITEMS, run offset and latest head carried along
@@ -560,7 +522,10 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
     TC_TRY(ws_alloc(ctx, tiles, &tj));
     TC_TRY(ws_alloc(ctx, tiles, &toff));
     TC_TRY(ws_alloc(ctx, 2, &d_R));
-    if (tiled) {
+    if (tiled && link->scanned) { // the replay kernel's last CTA has scanned the tile records already
+        toff = link->d_toff;
+        th = link->d_theadx;
+    } else if (tiled) {
         TC_LAUNCH(ctx, rle_tstat_scan_kernel, 1, 1024, 0, link->d_tstat, tiles, link->tile_syms, toff, th);
     } else {
         TC_LAUNCH(ctx, (rle_reduce_kernel<In>), (unsigned)tiles, RT, 0, in, N, tp, th, tj);
