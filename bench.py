@@ -334,6 +334,14 @@ def run_b200(args):
         e_steps = args.steps
         e2e_records, d2h_records = timed_batch(False)
         e2e_val, d2h = timed_batch(True)
+        # the same call over 4 x steps blocks: the first H2D and the last D2H of a call are not overlapped with
+        # anything, which a 10-block call shows as ~15 % and a long one does not
+        LONG = 4 * args.steps
+        barrier()
+        t0 = time.perf_counter()
+        batch(LONG, True)
+        torch.cuda.synchronize()
+        e2e_long = LONG * n / 1e6 / (time.perf_counter() - t0)
         # the container of the last block must unpack to runs that cover its BWT
         last = h_out[(e_steps - 1) % NH]
         uinfo = BlockInfo()
@@ -419,7 +427,8 @@ def run_b200(args):
                     "api": "tc_blocks_encode_packed: one call over `steps` blocks, pinned host buffers in and out, "
                            "copies of neighbouring blocks overlapped with compute, three blocks in flight (lanes: contexts + "
                            "host threads inside the call); output = packed block container "
-                           "(header + runs at 2 B + 1 bit each, lossless: tc_packed_unpack returns the records)",
+                           "(header + runs at 1.625 B each, lossless: tc_packed_unpack returns the records)",
+                    "long_call_MBps_this_rank": e2e_long, "long_call_blocks": LONG,
                     "record_output_MBps": e2e_records, "record_output_d2h_bytes_per_step": d2h_records,
                     "single_block_call_MBps": e2e_single, "cpu_affinity_bound_to_gpu": bool(numa_bound)},
             "gpu_launches": int(launches),

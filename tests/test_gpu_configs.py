@@ -8,7 +8,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from tests.util import gen_acgtn, gen_ascii, gen_bytes, gen_reads
+from tests.util import gen_acgtn, gen_ascii, gen_bytes, gen_reads, gen_words
 
 pytestmark = pytest.mark.gpu
 
@@ -243,3 +243,33 @@ def test_raw_byte_keys_vs_oracle(ctx, orc):
             g[primary.value] = -1
             _same("bwt", g, o_bwt)
     ctx2.close()
+
+
+def _python_corpus(nbytes):
+    """Concatenated Python sources of this interpreter's site-packages (the corpus of tools/real_text.py): real,
+    correlated, repetitive text.  The same image runs on the GPU box, so the corpus is there too."""
+    import glob
+    import sysconfig
+    buf = bytearray()
+    for f in sorted(glob.glob(sysconfig.get_paths()["purelib"] + "/**/*.py", recursive=True)):
+        try:
+            buf += open(f, "rb").read()
+        except OSError:
+            pass
+        if len(buf) >= nbytes:
+            break
+    return np.frombuffer(bytes(buf[:nbytes]), dtype=np.uint8)
+
+
+def test_correlated_text_vs_oracle(ctx, orc):
+    """Correlated text leaves the uniform-key suffix sort (oversized buckets, deep ties) for the LSD + prefix-doubling
+    path with many rounds; MTF indices are mostly 0 and runs are long.  Synthetic word text with verbatim repeats, and
+    1 MiB / 4 MiB slices of real Python sources, every stage against the oracle."""
+    _check_block(ctx, orc, gen_words(0x9C, 1 << 20))
+    _check_block(ctx, orc, gen_words(0x9D, (3 << 20) + 12345, dup_every=1 << 16, dup_len=20000), both_chains=False)
+    corpus = _python_corpus(6 << 20)
+    if corpus.size < (6 << 20):
+        pytest.skip("site-packages holds less than 6 MiB of Python sources")
+    _check_block(ctx, orc, corpus[: 1 << 20])
+    _check_block(ctx, orc, corpus[5 << 20:], both_chains=False)
+    _check_block(ctx, orc, corpus[1 << 20: 5 << 20], both_chains=False)

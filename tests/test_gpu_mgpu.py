@@ -65,3 +65,70 @@ def test_fm_replicate_and_sharded_queries_vs_oracle(orc):
             assert pos[int(ho[i]):int(ho[i + 1])].tolist() == ofm.locate(p).tolist(), (devs, i)
         reps.close()
     fm.close()
+
+
+def _nccl_worker(rank, world, port, out):
+    """One process per GPU: index built on rank 0, image broadcast over NCCL (multi.build_replicated), each rank
+    counts its contiguous chunk with tc_fm_count_dev, counts gathered in input order."""
+    import ctypes as C
+    import os
+    import sys
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    from tests.util import gen_acgtn, gen_reads
+    from text_compression_b200 import _lib, multi
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        ctx = _lib.Context(rank)
+        text = gen_acgtn(0xC3, 400_000)
+        d_text = torch.from_numpy(text).cuda()
+        fm = multi.build_replicated(ctx, d_text, text.size, 16)
+        assert int(fm.info.n) == text.size
+        reads = gen_reads(0xC3 + 7, text, 5_003, 24)
+        q = reads.shape[0]
+        lo, hi = multi.query_slice(q, world, rank)
+        mine = np.ascontiguousarray(reads[lo:hi])
+        d_pats = torch.from_numpy(mine.reshape(-1)).cuda()
+        d_off = (torch.arange(hi - lo + 1, dtype=torch.int64, device="cuda") * reads.shape[1])
+        d_cnt = torch.empty(hi - lo, dtype=torch.int64, device="cuda")
+        ctx.call("tc_fm_count_dev", fm.h, C.c_void_p(d_pats.data_ptr()), C.c_void_p(d_off.data_ptr()), hi - lo,
+                 C.c_void_p(d_cnt.data_ptr()))
+        torch.cuda.synchronize()
+        full = multi.gather_in_order(d_cnt.cpu().numpy(), q)
+        if rank == 0:
+            out.put(full.tolist())
+        fm.close()
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_build_replicated_and_sharded_count_vs_oracle(orc):
+    """World size 2 over NCCL (needs two GPUs: `gpurun --gpus 2`): the replicated index answers like the oracle."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mctx = mp.get_context("spawn")
+    out = mctx.Queue()
+    procs = [mctx.Process(target=_nccl_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    text = gen_acgtn(0xC3, 400_000)
+    reads = gen_reads(0xC3 + 7, text, 5_003, 24)
+    ofm = orc.FMIndex(text)
+    want = [ofm.count(r.tobytes()) for r in reads]
+    assert got == want

@@ -29,6 +29,32 @@ def gen_ascii(seed, n):
     return (0x20 + (splitmix64(seed, n) >> np.uint64(33)) % np.uint64(95)).astype(np.uint8)
 
 
+def gen_words(seed, n, vocab=600, dup_every=1 << 18, dup_len=6000):
+    """Correlated, repetitive text: Zipf-like draws from a fixed vocabulary of short lower-case words, indented
+    lines, and a block copied verbatim from earlier in the text every `dup_every` bytes (long common prefixes,
+    like duplicated files in a source tree).  Deterministic."""
+    r = splitmix64(seed, 4 * vocab + n // 2 + 16)
+    words = []
+    for w in range(vocab):
+        ln = 2 + int(r[4 * w] % np.uint64(9))
+        letters = (r[4 * w + 1] >> (np.arange(ln, dtype=np.uint64) * np.uint64(5))) % np.uint64(26)
+        words.append(bytes((0x61 + letters).astype(np.uint8)))
+    out = bytearray()
+    k = 4 * vocab
+    next_dup = dup_every
+    while len(out) < n:
+        x = int(r[k]); k += 1
+        u = (x >> 11) / float(1 << 53)
+        out += words[int(vocab * u * u * u)]          # cubic skew: a few words dominate
+        sep = (x >> 3) & 31
+        out += b"\n        " if sep == 0 else b"\n    " if sep == 1 else b"." if sep == 2 else b" "
+        if len(out) >= next_dup:
+            src = (x >> 17) % (len(out) - dup_len)
+            out += out[src: src + dup_len]
+            next_dup += dup_every
+    return np.frombuffer(bytes(out[:n]), dtype=np.uint8).copy()
+
+
 def gen_reads(seed, text, q, m, mut_frac=0.10):
     """q reads of m symbols at uniform offsets; mut_frac of them get one random substitution."""
     r = splitmix64(seed, 3 * q)

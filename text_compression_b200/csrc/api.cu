@@ -282,6 +282,8 @@ int compress_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, bool with_mtf, 
     TC_TRY(ws_alloc(ctx, ceil_div_u64(N, 4096) + 1, &link.d_toff));
     TC_TRY(ws_alloc(ctx, ceil_div_u64(N, 4096) + 1, &link.d_theadx));
     TC_TRY(ws_alloc(ctx, 2, &link.d_ticket));
+    TC_TRY(ws_alloc(ctx, MtfRleLink::SMALL_WORDS, &link.d_R)); // run count, exception count and the final list: one copy back
+    link.d_final = reinterpret_cast<uint16_t *>(link.d_R + MtfRleLink::H_FINAL);
     TC_TRY(mtf_encode_u8_dev_impl(ctx, d_bwt, N, info->primary, d_idx, info->final_list, &info->sigma, present, &link));
     int rc = rle_encode_u16_dev_impl(ctx, d_idx, N, d_count, d_rsym, cap, &info->R, pk, &link); // syncs the stream
     int rc2 = mtf_finish_pending(ctx);
@@ -381,7 +383,7 @@ extern "C" int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *co
     }
     // everything queued earlier on the context's stream must be done before the copy streams touch the arena
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    bool d2h_pending[2] = {false, false};
+    bool d2h_pending[2] = {false, false}, slot_filled[2] = {false, false};
     int rc_all = TC_OK;
     auto issue_h2d = [&](uint64_t b) -> int {
         const int s = (int)(b & 1);
@@ -602,12 +604,14 @@ int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain
         TC_TRY(ws_alloc(ctx, pk[s].big_cap, &pk[s].big_cnt));
     }
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    bool d2h_pending[2] = {false, false};
+    bool d2h_pending[2] = {false, false}, slot_filled[2] = {false, false};
     int rc_all = TC_OK;
     auto issue_h2d = [&](uint64_t b, int s) -> int {
         std::lock_guard<std::mutex> g(chain.m);
         if (chain.last) TC_CUDA(cudaStreamWaitEvent(ctx->s_h2d, chain.last, 0));
-        if (n[b]) TC_CUDA(cudaMemcpyAsync(d_text[s], text[b], n[b], cudaMemcpyHostToDevice, ctx->s_h2d));
+        if (n[b] && !((ctx->diag & 1) && slot_filled[s]))
+            TC_CUDA(cudaMemcpyAsync(d_text[s], text[b], n[b], cudaMemcpyHostToDevice, ctx->s_h2d));
+        slot_filled[s] = true;
         TC_CUDA(cudaEventRecord(ctx->ev_h2d[s], ctx->s_h2d));
         chain.last = ctx->ev_h2d[s];
         return TC_OK;
@@ -646,7 +650,7 @@ int blocks_packed_lane(tc_ctx *ctx, std::atomic<uint64_t> &next, H2dChain &chain
         // every section is copied at its exact length and its tail up to the next section is
         // zeroed on the host, so every byte of the container is defined
         auto section = [&](uint64_t off, const void *d_src, uint64_t len, uint64_t next) -> int {
-            if (len) TC_CUDA(cudaMemcpyAsync(o + off, d_src, len, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (len && !(ctx->diag & 2)) TC_CUDA(cudaMemcpyAsync(o + off, d_src, len, cudaMemcpyDeviceToHost, ctx->s_d2h));
             memset(o + off + len, 0, next - off - len);
             return TC_OK;
         };

@@ -40,6 +40,7 @@ struct tc_ctx {
         uint32_t sigma = 0;
         int16_t alpha[257];
         int16_t *final_list = nullptr;
+        uint32_t h_off = 512; // where in h_scal (64-bit words) the device list lands
     } mtf_pending;
     uint32_t text_hist[256] = {0}; // byte histogram of the last text handed to the suffix sort
     // extra lanes of the batch entry points (tc_blocks_encode_packed / _dev): full contexts of their
@@ -52,6 +53,7 @@ struct tc_ctx {
     bool mtf_v2 = false; // TC_B200_MTF_V2=1: warp-per-chunk MTF replay (the round-1 kernel) instead of thread-per-chunk
     uint32_t mtf_L = 0;  // TC_B200_MTF_L: chunk length of the thread-per-chunk MTF replay (0 = one chunk per resident thread)
     void *mtf_auto[9] = {nullptr}; // per alphabet size: device tables of the MTF automata (mtf.cu: AutoTables)
+    uint32_t diag = 0;   // TC_B200_DIAG (ctx.cu): timing experiments only, results are then incomplete
     uint32_t attr_done = 0; // kernels whose dynamic shared-memory limit has been raised on this context's device
     char err[512] = {0};
     // optional per-kernel timing (tc_ctx_profile): one event pair per launch

@@ -54,6 +54,8 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     ctx->mtf_v2 = m2 && m2[0] == '1';
     const char *ml = getenv("TC_B200_MTF_L");
     if (ml) ctx->mtf_L = (uint32_t)atoi(ml);
+    const char *dg = getenv("TC_B200_DIAG"); // measurement only: 1 = packed batch without its H2D copies (after each slot's first), 2 = without its D2H copies
+    ctx->diag = dg ? (uint32_t)atoi(dg) : 0;
     const char *ln = getenv("TC_B200_LANES");
     if (ln && ln[0] >= '1' && ln[0] <= '0' + tc_ctx::MAX_LANES) ctx->lanes = ln[0] - '0';
     if (have_stream) {

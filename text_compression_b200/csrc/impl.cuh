@@ -22,6 +22,11 @@ struct MtfRleLink {
     uint64_t ntiles = 0;      // set by the MTF stage
     uint32_t tile_syms = 0;   // symbols per tile
     bool valid = false;       // false: the MTF path taken does not collect them
+    // Small results of both stages in one device buffer so that ONE small copy at the end of the RLE stage brings
+    // them back: d_R[0] = runs, d_R[1] = exception count, then the final MTF list (257 x u16) at d_final.
+    uint64_t *d_R = nullptr;       // caller-allocated, SMALL_WORDS 64-bit words; d_final = (uint16_t *)(d_R + H_FINAL)
+    uint16_t *d_final = nullptr;
+    static constexpr uint32_t H_FINAL = 2, SMALL_WORDS = 2 + 66;
 };
 int mtf_encode_u8_dev_impl(tc_ctx *ctx, const uint8_t *d_bwt, uint64_t N, uint64_t primary, uint16_t *d_idx,
                            int16_t *final_list, uint32_t *sigma, const uint8_t *present_hint = nullptr,

@@ -1634,11 +1634,23 @@ __global__ void mtfd_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N,
 // The final list (ranks) comes back through the pinned scalars.  In the composed helpers
 // (`defer`) the host does not wait here: the RLE stage that follows syncs the stream anyway and
 // mtf_finish_pending() then translates the ranks.  Slot 512.. of h_scal is used by nothing else.
+// When the RLE stage shares its result words with the list (MtfRleLink::d_final), its one small copy brings the
+// list back too and none is launched here.
+static int final_buf(tc_ctx *ctx, const MtfRleLink *link, uint16_t **d_final) {
+    if (link && link->d_final) {
+        *d_final = link->d_final;
+        return TC_OK;
+    }
+    return ws_alloc(ctx, SIGMAX, d_final);
+}
 int mtf_read_final(tc_ctx *ctx, const uint16_t *d_final, uint32_t sigma, const int16_t *alpha, int16_t *final_list,
-                   bool defer, uint32_t nalpha = 0) { // alpha: device list entry -> symbol (nalpha entries, default sigma)
+                   bool defer, uint32_t nalpha = 0, const MtfRleLink *link = nullptr) {
+    // alpha: device list entry -> symbol (nalpha entries, default sigma)
     if (!nalpha) nalpha = sigma;
-    uint16_t *h_final = (uint16_t *)(ctx->h_scal + 512);
-    TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
+    const bool shared = defer && link && link->d_final == d_final;
+    ctx->mtf_pending.h_off = shared ? MtfRleLink::H_FINAL : 512;
+    uint16_t *h_final = (uint16_t *)(ctx->h_scal + ctx->mtf_pending.h_off);
+    if (!shared) TC_TRY(tc_d2h_small(ctx, h_final, d_final, sigma * sizeof(uint16_t)));
     if (defer) {
         ctx->mtf_pending.active = true;
         ctx->mtf_pending.sigma = sigma;
@@ -1780,7 +1792,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         TC_TRY(ws_alloc(ctx, ntiles * AU_T, &part));
         TC_TRY(ws_alloc(ctx, ntiles, &tot));
         TC_TRY(ws_alloc(ctx, ntiles, &start_list));
-        TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+        TC_TRY(final_buf(ctx, link, &d_final));
         const size_t sma = sizeof(AutoSmem);
         const uint32_t abit = sizeof(*src.p) == 1 ? 4u : 8u;
         if (!(ctx->attr_done & abit)) {
@@ -1804,7 +1816,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
                       (uint32_t *)nullptr);
         }
         *sigma_out = sigma;
-        int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
+        int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr, 0, link);
         tc_ws_release(ctx, mk);
         return rc;
     }
@@ -1816,14 +1828,14 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         TC_TRY(ws_alloc(ctx, ntiles * SM_T, &part));
         TC_TRY(ws_alloc(ctx, ntiles, &tot));
         TC_TRY(ws_alloc(ctx, ntiles, &start_list));
-        TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+        TC_TRY(final_buf(ctx, link, &d_final));
         ctx->prof_bytes_next = N * sizeof(*src.p);
         TC_LAUNCH(ctx, (mtfs_summary_kernel<Src>), (unsigned)ntiles, SM_T, 0, src, lut, N, part, tot);
         TC_LAUNCH(ctx, mtfs_top_kernel, 1, 1024, 0, tot, ntiles, sigma, start_list, d_final);
         ctx->prof_bytes_next = N * (sizeof(*src.p) + 2);
         TC_LAUNCH(ctx, (mtfs_replay_kernel<Src>), (unsigned)ntiles, SM_T, 0, src, lut, N, part, start_list, sigma, d_idx);
         *sigma_out = sigma;
-        int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
+        int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr, 0, link);
         tc_ws_release(ctx, mk);
         return rc;
     }
@@ -1842,7 +1854,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
         uint32_t *segpre;
         TC_TRY(ws_alloc(ctx, (size_t)T2_SEGS * R3_ROW, &segpre));
         const uint32_t seg_tiles = (uint32_t)std::max<uint64_t>(1, ceil_div_u64(ntiles, T2_SEGS));
-        TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+        TC_TRY(final_buf(ctx, link, &d_final));
         TC_TRY(ws_alloc(ctx, nchunks * R3_ROW, &start));
         uint32_t *ticket = finalocc + R3_ROW;
         Present pr;
@@ -1881,7 +1893,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
                       (uint32_t *)nullptr);
         }
         *sigma_out = sigma;
-        int rc = mtf_read_final(ctx, d_final, sigma, alpha_li, final_list, present_hint != nullptr, SIGMAX);
+        int rc = mtf_read_final(ctx, d_final, sigma, alpha_li, final_list, present_hint != nullptr, SIGMAX, link);
         tc_ws_release(ctx, mk);
         return rc;
     }
@@ -1897,7 +1909,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
     TC_TRY(ws_alloc(ctx, nchunks * VS, &lastocc));
     TC_TRY(ws_alloc(ctx, ntiles * VS, &tiletot));
     TC_TRY(ws_alloc(ctx, VSMAX, &finalocc));
-    TC_TRY(ws_alloc(ctx, SIGMAX, &d_final));
+    TC_TRY(final_buf(ctx, link, &d_final));
     unsigned cgrid = (unsigned)ceil_div_u64(nchunks, ENC_WARPS);
     TC_LAUNCH(ctx, (mtf2_lastocc_kernel<Src>), cgrid, ENC_WARPS * 32, 0, src, lut, N, L, nchunks, VS, lastocc);
     TC_LAUNCH(ctx, mtf2_scan_tiles_kernel, (unsigned)ntiles, VSMAX, 0, lastocc, nchunks, G, VS, tiletot);
@@ -1907,7 +1919,7 @@ int mtf_encode_impl(tc_ctx *ctx, Src src, uint64_t N, uint16_t *d_idx, int16_t *
               tiletot, d_idx);
     TC_LAUNCH(ctx, mtf2_final_kernel, 1, 32, 0, finalocc, N, sigma, VS, d_final);
     *sigma_out = sigma;
-    int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr);
+    int rc = mtf_read_final(ctx, d_final, sigma, alpha, final_list, present_hint != nullptr, 0, link);
     tc_ws_release(ctx, mk);
     return rc;
 }
@@ -1928,9 +1940,9 @@ void mtf_free_tables(tc_ctx *ctx) {
 int mtf_finish_pending(tc_ctx *ctx) {
     if (!ctx->mtf_pending.active) return TC_OK;
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    const uint16_t *h_final = (const uint16_t *)(ctx->h_scal + 512);
-    for (uint32_t j = 0; j < ctx->mtf_pending.sigma; j++)
-        ctx->mtf_pending.final_list[j] = ctx->mtf_pending.alpha[h_final[j]];
+    const uint16_t *h_final = (const uint16_t *)(ctx->h_scal + ctx->mtf_pending.h_off);
+    for (uint32_t j = 0; j < ctx->mtf_pending.sigma; j++) // (an RLE stage that failed before its copy leaves garbage here)
+        ctx->mtf_pending.final_list[j] = h_final[j] < SIGMAX ? ctx->mtf_pending.alpha[h_final[j]] : (int16_t)-1;
     ctx->mtf_pending.active = false;
     return TC_OK;
 }

@@ -521,7 +521,11 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
     TC_TRY(ws_alloc(ctx, tiles, &th));
     TC_TRY(ws_alloc(ctx, tiles, &tj));
     TC_TRY(ws_alloc(ctx, tiles, &toff));
-    TC_TRY(ws_alloc(ctx, 2, &d_R));
+    const bool shared = link && link->d_R; // result words shared with the MTF stage's final list (impl.cuh)
+    if (shared)
+        d_R = link->d_R;
+    else
+        TC_TRY(ws_alloc(ctx, 2, &d_R));
     if (tiled && link->scanned) { // the replay kernel's last CTA has scanned the tile records already
         toff = link->d_toff;
         th = link->d_theadx;
@@ -557,7 +561,7 @@ int rle_encode_impl(tc_ctx *ctx, In in, uint64_t N, uint32_t *d_count, int16_t *
         TC_LAUNCH(ctx, (rle_emit_kernel<In, false>), (unsigned)tiles, RT, 0, in, N, toff, th, tj, d_count, d_rsym, cap,
                   d_R, pa);
     }
-    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, (pk ? 2 : 1) * sizeof(uint64_t)));
+    TC_TRY(tc_d2h_small(ctx, ctx->h_scal, d_R, (shared ? MtfRleLink::SMALL_WORDS : pk ? 2 : 1) * sizeof(uint64_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     *R = ctx->h_scal[0];
     tc_ws_release(ctx, mk);

@@ -418,10 +418,14 @@ __global__ void __launch_bounds__(PC_T)
 // level-2 bucket starts: one CTA per segment scans the segment's digit counts
 __global__ void __launch_bounds__(256)
     starts_kernel(const uint32_t *__restrict__ hist2, const uint32_t *__restrict__ segstart, uint32_t nb2,
-                  uint32_t nbk, uint64_t n, uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor) {
+                  uint32_t nbk, uint64_t n, uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor,
+                  uint32_t bucket_cap, uint32_t *__restrict__ overflow) {
     __shared__ uint32_t sh[256 / 32 + 1];
     const uint32_t s = blockIdx.x, d = threadIdx.x;
     uint32_t c = d < nb2 ? hist2[s * nb2 + d] : 0;
+    // a bucket the final level cannot hold: the level-2 partition and the final sort return at once and the host
+    // takes the other sort path (correlated text ends here 0.4 ms earlier than by overflowing in the final sort)
+    if (c > bucket_cap) atomicOr(overflow, 1u);
     uint32_t ex = segstart[s] + block_excl_sum<uint32_t, 256>(c, sh, (uint32_t *)nullptr);
     if (d < nb2) {
         starts[s * nb2 + d] = ex;
@@ -448,9 +452,10 @@ __global__ void __launch_bounds__(PT_T, 6)
     part_kernel(const uint32_t *__restrict__ ukey_in, const uint8_t *__restrict__ text, int packprev,
                 const uint2 *__restrict__ rec_in, uint2 *__restrict__ rec_out, uint64_t n, int shift, uint32_t dmask,
                 const uint32_t *__restrict__ segstart, const uint32_t *__restrict__ tilebase, int nseg,
-                uint32_t *__restrict__ cursor) {
+                uint32_t *__restrict__ cursor, const uint32_t *__restrict__ stop) {
     extern __shared__ __align__(16) unsigned char pt_raw[];
     PtSmem &S = *reinterpret_cast<PtSmem *>(pt_raw);
+    if (stop && *stop) return; // an oversized bucket was seen (starts_kernel)
     const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
@@ -933,12 +938,12 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         uint32_t *ukey, *hist1, *hist2, *segstart, *cursor1, *tilebase, *chunkbase, *starts2, *cursor2, *flags;
         uint2 *recA, *recB = nullptr;
         uint64_t *d_primary = nullptr;
-        if (d_bwt) TC_TRY(ws_alloc(ctx, 1, &d_primary));
         TC_TRY(ws_alloc(ctx, (size_t)1 << gb, &uk_lut));
         TC_TRY(ws_alloc(ctx, n, &ukey));
         TC_TRY(ws_alloc(ctx, 256 + (size_t)nbk + 8, &hist1)); // hist1 | hist2 | flags: one memset
         hist2 = hist1 + 256;
-        flags = hist2 + nbk;
+        flags = hist2 + ((nbk + 1) & ~(size_t)1);
+        d_primary = reinterpret_cast<uint64_t *>(flags + 2); // next to the flags: one small copy brings both back
         TC_TRY(ws_alloc(ctx, 257, &segstart));
         TC_TRY(ws_alloc(ctx, 256, &cursor1));
         TC_TRY(ws_alloc(ctx, 257, &tilebase));
@@ -973,18 +978,19 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         ctx->prof_bytes_next = 4 * n + (packprev ? n : 0) + 8 * n;
         TC_LAUNCH(ctx, part_kernel<true>, (unsigned)ceil_div_u64(n, PT_TILE), PT_T, sizeof(PtSmem), ukey, d_text, packprev,
                   (const uint2 *)nullptr, recA, n, 32 - B1, (uint32_t)(nb1 - 1), (const uint32_t *)nullptr,
-                  (const uint32_t *)nullptr, 1, cursor1);
+                  (const uint32_t *)nullptr, 1, cursor1, (const uint32_t *)nullptr);
         const uint2 *recF = recA;
         const uint32_t *startsF = segstart;
         if (B2) {
             ctx->prof_bytes_next = 8 * n;
             TC_LAUNCH(ctx, seg_hist_kernel, (unsigned)ceil_div_u64(ceil_div_u64(n, PC_WCHUNK) + nb1, PC_WARPS), PC_T,
                       PC_SMEM, recA, segstart, chunkbase, nb1, 32 - PB, (uint32_t)(nb2 - 1), hist2);
-            TC_LAUNCH(ctx, starts_kernel, nb1, 256, 0, hist2, segstart, (uint32_t)nb2, nbk, n, starts2, cursor2);
+            TC_LAUNCH(ctx, starts_kernel, nb1, 256, 0, hist2, segstart, (uint32_t)nb2, nbk, n, starts2, cursor2,
+                      (uint32_t)FS_CAP, flags + FL_OVERFLOW);
             ctx->prof_bytes_next = 16 * n;
             TC_LAUNCH(ctx, part_kernel<false>, (unsigned)(ceil_div_u64(n, PT_TILE) + nb1), PT_T, sizeof(PtSmem),
                       (const uint32_t *)nullptr, (const uint8_t *)nullptr, 0, (const uint2 *)recA, recB, n, 32 - PB,
-                      (uint32_t)(nb2 - 1), segstart, tilebase, nb1, cursor2);
+                      (uint32_t)(nb2 - 1), segstart, tilebase, nb1, cursor2, (const uint32_t *)(flags + FL_OVERFLOW));
             recF = recB;
             startsF = starts2;
         }
@@ -993,16 +999,14 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         ctx->prof_bytes_next = 8 * n + 4 * n + (d_bwt ? n : 0);
         TC_LAUNCH(ctx, final_sort_kernel, (unsigned)ceil_div_u64(nbk, FS_WARPS), FS_WARPS * 32, 0, recF, startsF, nbk,
                   32 - PB, pw, b, kb, k, n, packprev, d_text, d_sa, d_bwt, d_primary, flags);
-        TC_TRY(tc_d2h_small(ctx, hU, flags, 2 * sizeof(uint32_t)));
-        if (d_bwt)
-            TC_TRY(tc_d2h_small(ctx, ctx->h_scal + 8, d_primary, sizeof(uint64_t)));
+        TC_TRY(tc_d2h_small(ctx, hU, flags, 4 * sizeof(uint32_t)));
         TC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (hU[FL_OVERFLOW] == 0) {
             sorted = true;
             if (hU[FL_TIES] == 0) { // every suffix is already distinguished by its key: done
                 if (bwt_done && d_bwt) {
                     *bwt_done = true;
-                    if (primary) *primary = ctx->h_scal[8];
+                    if (primary) *primary = ctx->h_scal[1];
                 }
                 tc_ws_release(ctx, mk);
                 return TC_OK;
@@ -1065,6 +1069,7 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
                 return TC_E_CUDA;
             }
             const unsigned gridU = (unsigned)ceil_div_u64(U, 256);
+            if (ctx->diag & 4) fprintf(stderr, "[tc_b200] doubling round %d: h = %llu, unresolved %llu of %llu\n", round, (unsigned long long)h, (unsigned long long)U, (unsigned long long)N);
             if (round == 0) {
                 TC_LAUNCH(ctx, sa_keys2_lookup_kernel, gridU, 256, 0, cjA, U, d_sa, keys, N, g, h, n, pw, b, kb, rb, key2a,
                           val2a);
