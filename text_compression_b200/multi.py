@@ -32,6 +32,9 @@ def bind_to_gpu_cpus(gpu_index: int) -> bool:
     ranks' copy-issuing threads do not fight for the same cores.  One process per GPU; call before allocating
     pinned memory.  Returns False if NVML is unavailable or nothing useful can be done."""
     import os
+    mode = os.environ.get("TC_B200_BIND", "slice")   # slice (default) | shared (NVML's set as is) | none
+    if mode == "none":
+        return False
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -48,7 +51,7 @@ def bind_to_gpu_cpus(gpu_index: int) -> bool:
             return False
         sharers = [i for i in range(pynvml.nvmlDeviceGetCount()) if affinity(i) == mine]
         cpus = sorted(mine)
-        if len(sharers) > 1:
+        if len(sharers) > 1 and mode == "slice":
             per = len(cpus) // len(sharers)
             if per >= 4:                       # fewer than 4 cores per rank: leave the scheduler alone
                 j = sharers.index(gpu_index)
