@@ -273,3 +273,46 @@ def test_correlated_text_vs_oracle(ctx, orc):
     _check_block(ctx, orc, corpus[: 1 << 20])
     _check_block(ctx, orc, corpus[5 << 20:], both_chains=False)
     _check_block(ctx, orc, corpus[1 << 20: 5 << 20], both_chains=False)
+
+
+def test_mtf_decode_kernels_agree(ctx, orc):
+    """seqFromMTF for alphabets of 9..257 symbols: the select-based kernels (default) and the list-shifting ones
+    (TC_B200_MTFD_V1=1) against the oracle -- uniform indices (the worst case of list shifting), mostly-zero indices,
+    always-the-back, with and without Nothing in the alphabet, sizes around the chunk and tile boundaries; an index
+    beyond the list is the reference's `index out of bounds` in both."""
+    import os
+    from text_compression_b200 import _lib
+    from text_compression_b200._lib import TC_E_INDEX, ptr
+    os.environ["TC_B200_MTFD_V1"] = "1"
+    try:
+        ctx1 = _lib.Context(0)
+    finally:
+        del os.environ["TC_B200_MTFD_V1"]
+    rng = np.random.default_rng(1234)
+    for n in (1, 7, 8, 9, 31, 223, 224, 225, 4097, 35_841, 160 * 224 + 5, 1_000_003, 5_000_001):
+        for sigma, mode, nothing in ((9, "uniform", True), (33, "zeros", False), (64, "back", True), (200, "uniform", False),
+                                     (256, "small", True), (257, "uniform", True), (257, "back", True)):
+            syms = np.sort(rng.choice(256, size=sigma - (1 if nothing else 0), replace=False)).astype(np.int16)
+            fin = np.concatenate([np.array([-1], np.int16), syms]) if nothing else syms
+            fin = fin[rng.permutation(fin.size)]          # any order: only the set matters (the decoder re-sorts it)
+            if mode == "uniform":
+                idx = rng.integers(0, sigma, size=n)
+            elif mode == "zeros":
+                idx = np.where(rng.random(n) < 0.9, 0, rng.integers(0, sigma, size=n))
+            elif mode == "small":
+                idx = np.minimum(rng.geometric(0.4, size=n) - 1, sigma - 1)
+            else:
+                idx = np.full(n, sigma - 1)
+            idx = np.ascontiguousarray(idx, dtype=np.uint16)
+            want = orc.mtf_decode(idx, fin)
+            for c in (ctx, ctx1):
+                out = np.empty(n, dtype=np.int16)
+                c.call("tc_mtf_decode", ptr(idx), n, ptr(fin), fin.size, ptr(out))
+                _same(f"mtf decode n={n} sigma={sigma} {mode}", out, want)
+    idx = np.zeros(70_000, dtype=np.uint16)
+    idx[54_321] = 40
+    fin = np.arange(40, dtype=np.int16)
+    for c in (ctx, ctx1):
+        out = np.empty(idx.size, dtype=np.int16)
+        assert c.L.tc_mtf_decode(c.h, ptr(idx), idx.size, ptr(fin), fin.size, ptr(out)) == TC_E_INDEX
+    ctx1.close()

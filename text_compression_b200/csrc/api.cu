@@ -383,7 +383,7 @@ extern "C" int tc_blocks_encode(tc_ctx *ctx, uint64_t nblocks, const uint8_t *co
     }
     // everything queued earlier on the context's stream must be done before the copy streams touch the arena
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
-    bool d2h_pending[2] = {false, false}, slot_filled[2] = {false, false};
+    bool d2h_pending[2] = {false, false};
     int rc_all = TC_OK;
     auto issue_h2d = [&](uint64_t b) -> int {
         const int s = (int)(b & 1);

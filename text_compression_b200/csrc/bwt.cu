@@ -10,11 +10,14 @@
 #include <algorithm>
 #include <utility>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "impl.cuh"
 
 int tc_byte_hist_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint32_t *h_hist);
 
+namespace cg = cooperative_groups;
 namespace {
 __global__ void bwt_emit_kernel(const uint8_t *__restrict__ t, const uint32_t *__restrict__ sa, uint64_t N,
                                 uint8_t *__restrict__ bwt, uint64_t *__restrict__ d_primary,
@@ -173,8 +176,9 @@ struct CStart {
 constexpr uint32_t NIL = 0xffffffffu;
 
 // sub-list of splitter s: rows s*K, psi(s*K), ... up to (excluding) the next splitter row
+// link[s] = (next splitter, hops to it), one 8-byte word per splitter: a jump round is one random access, not two
 __global__ void inv_walk1_kernel(const uint32_t *__restrict__ psi, uint64_t S, uint32_t K, uint64_t N,
-                                 uint32_t *__restrict__ nxt, uint32_t *__restrict__ dist) {
+                                 uint2 *__restrict__ link) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     uint32_t cur = (uint32_t)(s * K);
@@ -182,61 +186,103 @@ __global__ void inv_walk1_kernel(const uint32_t *__restrict__ psi, uint64_t S, u
     do {
         cur = psi[cur];
         cnt++;
-    } while (cur % K != 0 && cnt <= N); // psi is a permutation: the walk returns to a splitter within N steps
+    } while ((cur & (K - 1)) != 0 && cnt <= N); // psi is a permutation: the walk returns to a splitter within N steps
     uint32_t succ = cur / K;
-    nxt[s] = succ == 0 ? NIL : succ; // the cycle through row 0 is cut just before row 0
-    dist[s] = cnt;
+    link[s] = make_uint2(succ == 0 ? NIL : succ, cnt); // the cycle through row 0 is cut just before row 0
 }
-
-// one pointer-jumping round (double buffered)
-__global__ void inv_jump_kernel(const uint32_t *__restrict__ nxt, const uint32_t *__restrict__ dist, uint64_t S,
-                                uint32_t *__restrict__ nxt2, uint32_t *__restrict__ dist2) {
-    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    uint32_t nx = nxt[s];
-    uint32_t d = dist[s];
-    if (nx != NIL) {
-        d += dist[nx];
-        nx = nxt[nx];
+__device__ __forceinline__ uint2 inv_jump_one(const uint2 *__restrict__ a, uint64_t s) {
+    uint2 v = a[s];
+    if (v.x != NIL) {
+        const uint2 u = a[v.x];
+        v.y += u.y;
+        v.x = u.x;
     }
-    nxt2[s] = nx;
-    dist2[s] = d;
+    return v;
 }
-
-// second walk: splitter s starts `total - dist[s]` steps after row 0
-__global__ void inv_walk2_kernel(const uint32_t *__restrict__ psi, uint64_t S, uint32_t K,
-                                 const uint32_t *__restrict__ nxt_final, const uint32_t *__restrict__ dist_final,
-                                 CStart cs, uint8_t *__restrict__ text, uint64_t cap, uint64_t N,
-                                 uint32_t *__restrict__ err) {
-    __shared__ uint32_t sc[258];
-    for (int j = threadIdx.x; j < 258; j += blockDim.x) sc[j] = cs.c[j];
-    __syncthreads();
+__global__ void inv_jump_kernel(const uint2 *__restrict__ a, uint64_t S, uint2 *__restrict__ b) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) b[s] = inv_jump_one(a, s);
+}
+// All pointer-jumping rounds in one cooperative launch (a grid barrier between rounds instead of ~20 launches of
+// ~10 us each).  The result of `rounds` rounds is in (rounds odd ? b : a).
+__global__ void __launch_bounds__(512)
+    inv_jump_all_kernel(uint2 *a, uint2 *b, uint64_t S, int rounds) {
+    cg::grid_group grid = cg::this_grid();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < rounds; r++) {
+        const uint2 *src = (r & 1) ? b : a;
+        uint2 *dst = (r & 1) ? a : b;
+        for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += stride) {
+            uint2 v = __ldcg(&src[s]); // written by other SMs in the round before: L2, not L1
+            if (v.x != NIL) {
+                const uint2 u = __ldcg(&src[v.x]);
+                v.y += u.y;
+                v.x = u.x;
+            }
+            dst[s] = v;
+        }
+        grid.sync();
+    }
+}
+// Text positions -> rows: every splitter on the cycle through row 0 walks its segment and files the rows it passes
+// under their text position.  Walk lengths are geometric, so lanes idle while the longest walk of their warp
+// finishes: this loop is therefore kept to a load, a store and a test, and the per-position work (which symbol owns
+// the row) is done afterwards by inv_text_kernel, one position per thread, without divergence.
+__global__ void inv_rows_kernel(const uint32_t *__restrict__ psi, uint64_t S, uint32_t K,
+                                const uint2 *__restrict__ link, uint32_t *__restrict__ row_at, uint64_t N) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    if (nxt_final[s] != NIL) return; // not on the cycle through row 0
-    uint64_t total = dist_final[0];
-    uint64_t g = total - dist_final[s];
+    const uint2 me = link[s];
+    if (me.x != NIL) return; // not on the cycle through row 0
+    const uint64_t total = link[0].y;
+    uint64_t g = total - me.y;
     uint32_t cur = (uint32_t)(s * K);
-    bool first = true;
     uint64_t guard = 0;
-    while ((first || cur % K != 0) && guard++ <= N) {
-        first = false;
-        if (g >= 1) {
-            // F[cur]: the code whose row range contains cur
-            int lo = 0, hi = 257; // sc[lo] <= cur < sc[hi]
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (sc[mid] <= cur) lo = mid; else hi = mid;
-            }
-            if (lo == 0) {
-                atomicMax(err, 1u); // fromJust Nothing (src/Data/BWT/Internal.hs:195)
-            } else if (g - 1 < cap) {
-                text[g - 1] = (uint8_t)(lo - 1);
-            }
-        }
+    do {
+        if (g >= 1 && g - 1 < N) row_at[g - 1] = cur;
         cur = psi[cur];
         g++;
+    } while ((cur & (K - 1)) != 0 && guard++ <= N);
+}
+// text[i] = F[row_at[i]]: the code whose row range contains the row; bucket table over the row's high bits, then
+// a binary search between the bucket's two ends (usually zero or one step).
+constexpr int IT_BUCKETS = 1024;
+__global__ void __launch_bounds__(256)
+    inv_text_kernel(const uint32_t *__restrict__ row_at, const uint2 *__restrict__ link, CStart cs, int sh,
+                    uint8_t *__restrict__ text, uint64_t cap, uint32_t *__restrict__ err) {
+    __shared__ uint32_t sc[258];
+    __shared__ uint16_t bt[IT_BUCKETS + 1];
+    for (int j = threadIdx.x; j < 258; j += blockDim.x) sc[j] = cs.c[j];
+    __syncthreads();
+    for (int bkt = threadIdx.x; bkt <= IT_BUCKETS; bkt += blockDim.x) {
+        const uint64_t x = (uint64_t)bkt << sh; // largest code index whose start is <= x (256 once x is past the rows)
+        int lo = 0, hi = 257;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint64_t)sc[mid] <= x) lo = mid; else hi = mid;
+        }
+        bt[bkt] = (uint16_t)lo;
     }
+    __syncthreads();
+    const uint64_t total = link[0].y; // rows on the cycle through row 0, the sentinel's included
+    const uint64_t n_out = total ? total - 1 : 0;
+    bool bad = false;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_out; i += (uint64_t)gridDim.x * blockDim.x * 4) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (i + q >= n_out) break;
+            const uint32_t cur = row_at[i + q];
+            const uint32_t bkt = cur >> sh;
+            int lo = bt[bkt], hi = bt[bkt + 1] + 1;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sc[mid] <= cur) lo = mid; else hi = mid;
+            }
+            if (lo == 0) bad = true; // fromJust Nothing (src/Data/BWT/Internal.hs:195)
+            else if (i + q < cap) text[i + q] = (uint8_t)(lo - 1);
+        }
+    }
+    if (bad) atomicMax(err, 1u);
 }
 
 template <class Src>
@@ -272,27 +318,46 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
     ctx->prof_bytes_next = N * (sizeof(*src.p) + 4);
     TC_LAUNCH(ctx, (cs_scatter_kernel<Src>), (unsigned)tiles, CS_T, 0, src, N, hist, totals, tiles, psi);
     // list ranking
-    const uint32_t K = 32;
+    const uint32_t K = 16;
     const uint64_t S = ceil_div_u64(N, K);
-    uint32_t *nxtA, *nxtB, *dA, *dB;
-    TC_TRY(ws_alloc(ctx, S, &nxtA));
-    TC_TRY(ws_alloc(ctx, S, &nxtB));
-    TC_TRY(ws_alloc(ctx, S, &dA));
-    TC_TRY(ws_alloc(ctx, S, &dB));
+    uint2 *linkA, *linkB;
+    uint32_t *row_at;
+    TC_TRY(ws_alloc(ctx, S, &linkA));
+    TC_TRY(ws_alloc(ctx, S, &linkB));
+    TC_TRY(ws_alloc(ctx, N, &row_at));
     uint32_t *d_err;
     TC_TRY(ws_alloc(ctx, 1, &d_err));
     TC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream));
     const unsigned gridS = (unsigned)ceil_div_u64(S, 128);
-    TC_LAUNCH(ctx, inv_walk1_kernel, gridS, 128, 0, psi, S, K, N, nxtA, dA);
+    TC_LAUNCH(ctx, inv_walk1_kernel, gridS, 128, 0, psi, S, K, N, linkA);
     int rounds = 1;
     while ((1ull << rounds) < S) rounds++;
-    for (int r = 0; r < rounds; r++) {
-        TC_LAUNCH(ctx, inv_jump_kernel, gridS, 128, 0, nxtA, dA, S, nxtB, dB);
-        std::swap(nxtA, nxtB);
-        std::swap(dA, dB);
+    if (ctx->coop_ok) {
+        int per_sm = 0;
+        TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inv_jump_all_kernel, 512, 0));
+        if (per_sm > 2) per_sm = 2;
+        const unsigned cgrid = (unsigned)std::min<uint64_t>(ceil_div_u64(S, 512), (uint64_t)ctx->sm_count * std::max(per_sm, 1));
+        uint64_t S_arg = S;
+        void *args[] = {&linkA, &linkB, &S_arg, &rounds};
+        if (ctx->prof_on) ctx->prof_begin("inv_jump_all_kernel");
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)inv_jump_all_kernel, dim3(cgrid), dim3(512), args, 0, ctx->stream);
+        if (ctx->prof_on) ctx->prof_end();
+        ctx->launches++;
+        if (e != cudaSuccess) return ctx->fail(e, "inv_jump_all_kernel", __LINE__);
+        if (rounds & 1) std::swap(linkA, linkB);
+    } else {
+        for (int r = 0; r < rounds; r++) {
+            TC_LAUNCH(ctx, inv_jump_kernel, gridS, 128, 0, (const uint2 *)linkA, S, linkB);
+            std::swap(linkA, linkB);
+        }
     }
-    TC_LAUNCH(ctx, inv_walk2_kernel, gridS, 128, 0, psi, S, K, nxtA, dA, cs, d_text, cap, N, d_err);
-    TC_TRY(tc_d2h_small(ctx, h, dA, sizeof(uint32_t)));
+    TC_LAUNCH(ctx, inv_rows_kernel, gridS, 128, 0, psi, S, K, (const uint2 *)linkA, row_at, N);
+    int sh = 0;
+    while (((N - 1) >> sh) >= (uint64_t)IT_BUCKETS) sh++;
+    ctx->prof_bytes_next = 5 * N;
+    TC_LAUNCH(ctx, inv_text_kernel, (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256 * 4 * 4), 1u << 20), 256, 0,
+              (const uint32_t *)row_at, (const uint2 *)linkA, cs, sh, d_text, cap, d_err);
+    TC_TRY(tc_d2h_small(ctx, h, &linkA[0].y, sizeof(uint32_t)));
     TC_TRY(tc_d2h_small(ctx, h + 1, d_err, sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
     uint64_t total = h[0];

@@ -51,8 +51,10 @@ struct tc_ctx {
     bool no_msd = false; // TC_B200_NO_MSD=1: force the LSD suffix-sort path (tests exercise both)
     bool no_rawkey = false; // TC_B200_NO_RAWKEY=1: arithmetic-code uniform keys also for equiprobable bytes (tests compare both)
     bool mtf_v2 = false; // TC_B200_MTF_V2=1: warp-per-chunk MTF replay (the round-1 kernel) instead of thread-per-chunk
+    bool mtfd_v1 = false; // TC_B200_MTFD_V1=1: list-shifting MTF decode kernels (cost grows with the index) instead of the select-based ones
     uint32_t mtf_L = 0;  // TC_B200_MTF_L: chunk length of the thread-per-chunk MTF replay (0 = one chunk per resident thread)
     void *mtf_auto[9] = {nullptr}; // per alphabet size: device tables of the MTF automata (mtf.cu: AutoTables)
+    bool coop_ok = false; // the device supports cooperative launches (grid barriers inside a kernel)
     uint32_t diag = 0;   // TC_B200_DIAG (ctx.cu): timing experiments only, results are then incomplete
     uint32_t attr_done = 0; // kernels whose dynamic shared-memory limit has been raised on this context's device
     char err[512] = {0};

@@ -46,12 +46,15 @@ static int ctx_create_impl(int device, cudaStream_t stream, bool have_stream, tc
     tc_ctx *ctx = new tc_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->coop_ok = prop.cooperativeLaunch != 0 && !(getenv("TC_B200_NO_COOP") && getenv("TC_B200_NO_COOP")[0] == '1');
     const char *nm = getenv("TC_B200_NO_MSD");
     ctx->no_msd = nm && nm[0] == '1';
     const char *nr = getenv("TC_B200_NO_RAWKEY");
     ctx->no_rawkey = nr && nr[0] == '1';
     const char *m2 = getenv("TC_B200_MTF_V2");
     ctx->mtf_v2 = m2 && m2[0] == '1';
+    const char *d1 = getenv("TC_B200_MTFD_V1");
+    ctx->mtfd_v1 = d1 && d1[0] == '1';
     const char *ml = getenv("TC_B200_MTF_L");
     if (ml) ctx->mtf_L = (uint32_t)atoi(ml);
     const char *dg = getenv("TC_B200_DIAG"); // measurement only: 1 = packed batch without its H2D copies (after each slot's first), 2 = without its D2H copies

@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "impl.cuh"
+#include "mtfd_select.cuh"
 
 namespace {
 constexpr int SIGMAX = 257;
@@ -1559,10 +1560,23 @@ __global__ void __launch_bounds__(SM_T)
     }
 }
 
-// D2a: exclusive chain of permutations inside a tile: acc'[j] = acc[perm[j]].
+// D2a: exclusive chain of permutations inside a tile: acc'[j] = acc[perm[j]].  Rows of `perm` / `part` are
+// `in_stride` / `out_stride` entries apart.  Rows are loaded four steps ahead (a ring of registers): the chain itself
+// runs through shared memory only and does not wait for global loads.
+constexpr int CH_PER = (SIGMAX + 31) / 32;
+constexpr int CH_RING = 4;
+__device__ __forceinline__ void chain_load(uint16_t (&dst)[CH_PER], const uint16_t *__restrict__ row, bool ok, uint32_t sigma,
+                                           unsigned lane) {
+#pragma unroll
+    for (int q = 0; q < CH_PER; q++) {
+        const uint32_t j = lane + 32u * q;
+        dst[q] = (ok && j < sigma) ? row[j] : (uint16_t)0;
+    }
+}
 __global__ void __launch_bounds__(128)
     mtfd_tile_chain_kernel(const uint16_t *__restrict__ perm, uint64_t nchunks, uint32_t G, uint32_t sigma,
-                           uint16_t *__restrict__ part, uint16_t *__restrict__ tilesum, uint64_t ntiles) {
+                           uint16_t *__restrict__ part, uint16_t *__restrict__ tilesum, uint64_t ntiles,
+                           uint32_t in_stride, uint32_t out_stride) {
     __shared__ uint16_t bufs[4][2][LISTPAD];
     const int w = threadIdx.x >> 5;
     const unsigned lane = lane_id();
@@ -1571,16 +1585,30 @@ __global__ void __launch_bounds__(128)
     uint16_t *A = bufs[w][0], *B = bufs[w][1];
     for (int j = lane; j < (int)sigma; j += 32) A[j] = (uint16_t)j;
     __syncwarp();
-    uint64_t k0 = t * G, k1 = k0 + G < nchunks ? k0 + G : nchunks;
-    for (uint64_t k = k0; k < k1; k++) {
-        for (int j = lane; j < (int)sigma; j += 32) {
-            part[k * sigma + j] = A[j];
-            B[j] = A[perm[k * sigma + j]];
+    const uint64_t k0 = t * G, k1 = k0 + G < nchunks ? k0 + G : nchunks;
+    uint16_t ring[CH_RING][CH_PER];
+#pragma unroll
+    for (int u = 0; u < CH_RING; u++) chain_load(ring[u], perm + (k0 + u) * in_stride, k0 + u < k1, sigma, lane);
+    for (uint64_t kb = k0; kb < k1; kb += CH_RING) {
+#pragma unroll
+        for (int u = 0; u < CH_RING; u++) {
+            const uint64_t k = kb + u;
+            if (k < k1) { // uniform over the warp
+#pragma unroll
+                for (int q = 0; q < CH_PER; q++) {
+                    const uint32_t j = lane + 32u * q;
+                    if (j < sigma) {
+                        part[k * out_stride + j] = A[j];
+                        B[j] = A[ring[u][q]];
+                    }
+                }
+                __syncwarp();
+                uint16_t *tmp = A;
+                A = B;
+                B = tmp;
+                chain_load(ring[u], perm + (k + CH_RING) * in_stride, k + CH_RING < k1, sigma, lane);
+            }
         }
-        __syncwarp();
-        uint16_t *tmp = A;
-        A = B;
-        B = tmp;
     }
     for (int j = lane; j < (int)sigma; j += 32) tilesum[t * sigma + j] = A[j];
 }
@@ -1597,15 +1625,29 @@ __global__ void __launch_bounds__(32)
     int16_t *A = bufs[0], *B = bufs[1];
     for (int j = lane; j < (int)sigma; j += 32) A[j] = l0.sym[j];
     __syncwarp();
-    for (uint64_t t = 0; t < ntiles; t++) {
-        for (int j = lane; j < (int)sigma; j += 32) {
-            tileprefix[t * sigma + j] = A[j];
-            B[j] = A[tilesum[t * sigma + j]];
+    uint16_t ring[CH_RING][CH_PER];
+#pragma unroll
+    for (int u = 0; u < CH_RING; u++) chain_load(ring[u], tilesum + (uint64_t)u * sigma, (uint64_t)u < ntiles, sigma, lane);
+    for (uint64_t tb = 0; tb < ntiles; tb += CH_RING) {
+#pragma unroll
+        for (int u = 0; u < CH_RING; u++) {
+            const uint64_t t = tb + u;
+            if (t < ntiles) {
+#pragma unroll
+                for (int q = 0; q < CH_PER; q++) {
+                    const uint32_t j = lane + 32u * q;
+                    if (j < sigma) {
+                        tileprefix[t * sigma + j] = A[j];
+                        B[j] = A[ring[u][q]];
+                    }
+                }
+                __syncwarp();
+                int16_t *tmp = A;
+                A = B;
+                B = tmp;
+                chain_load(ring[u], tilesum + (t + CH_RING) * sigma, t + CH_RING < ntiles, sigma, lane);
+            }
         }
-        __syncwarp();
-        int16_t *tmp = A;
-        A = B;
-        B = tmp;
     }
 }
 
@@ -1629,6 +1671,176 @@ __global__ void mtfd_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N,
         if (r >= sigma) r = 0;
         out[i] = (int16_t)list_take16(lst, r);
     }
+}
+
+// ---- decode, sigma <= 257, index-independent cost: the select step of mtfd_select.cuh, thread per chunk ---------
+// The old kernels above shift a per-thread list, which costs the index value (mean 128 on high-entropy input: 425 M
+// warp instructions per pass over 16 Mi symbols); these cost ~90 instructions per symbol whatever the index.
+// State per thread, word-interleaved across the CTA (conflict-free for any per-thread index): 128 words of entry bytes
+// (one per slot) + 16 bitmap words.  A CTA of D3_CT threads is one tile of the composition chains (G = D3_CT).
+constexpr int D3_CT = 160;
+constexpr int D3_SYMW = d3::SLOTS / 4;
+constexpr int D3_WORDS = D3_SYMW + d3::WORDS; // 144 words = 576 B per thread
+constexpr int D3_STRIDE = 264;                // u16 entries per permutation row in global memory (16-byte multiple)
+constexpr int D3_G = 32;                      // chunks per tile of the composition chains (divides D3_CT)
+struct D3Smem {
+    uint32_t st[D3_WORDS * D3_CT];
+    int16_t q[D3_CT / D3_G][D3_STRIDE]; // replay: list at the start of each of the CTA's tiles
+    uint8_t sel8[2048];
+};
+struct D3State {
+    uint32_t *st; // &smem.st[threadIdx.x]
+    const uint8_t *lut;
+    __device__ __forceinline__ uint32_t bm_load(uint32_t w) const { return st[(D3_SYMW + w) * D3_CT]; }
+    __device__ __forceinline__ void bm_store(uint32_t w, uint32_t x) { st[(D3_SYMW + w) * D3_CT] = x; }
+    __device__ __forceinline__ uint32_t sym_load(uint32_t s) const {
+        return reinterpret_cast<const uint8_t *>(&st[(s >> 2) * D3_CT])[s & 3u];
+    }
+    __device__ __forceinline__ void sym_store(uint32_t s, uint32_t v) {
+        reinterpret_cast<uint8_t *>(&st[(s >> 2) * D3_CT])[s & 3u] = (uint8_t)v;
+    }
+    __device__ __forceinline__ uint32_t sel8(uint32_t i) const { return lut[i]; }
+};
+__device__ __forceinline__ void d3_fill_lut(uint8_t *lut) {
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) lut[i] = d3::sel8_entry(i >> 3, i & 7u);
+}
+// Walks the chunk's indices eight at a time (128-bit loads when the stream is 16-byte aligned), one load ahead:
+// f(i, index, q) with q = 0..7 the position inside a full group of eight (a compile-time constant after unrolling)
+// or q = 8 for positions outside full groups (chunk tail, unaligned streams).
+template <class F>
+__device__ __forceinline__ void d3_walk(const uint16_t *__restrict__ idx, uint64_t beg, uint64_t end, bool wide, F f) {
+    uint64_t i = beg;
+    if (wide) {
+        uint4 nx = make_uint4(0, 0, 0, 0);
+        if (i + 8 <= end) nx = *reinterpret_cast<const uint4 *>(idx + i);
+        while (i + 8 <= end) {
+            const uint4 v = nx;
+            if (i + 16 <= end) nx = *reinterpret_cast<const uint4 *>(idx + i + 8);
+            f(i + 0, v.x & 0xffffu, 0);
+            f(i + 1, v.x >> 16, 1);
+            f(i + 2, v.y & 0xffffu, 2);
+            f(i + 3, v.y >> 16, 3);
+            f(i + 4, v.z & 0xffffu, 4);
+            f(i + 5, v.z >> 16, 5);
+            f(i + 6, v.w & 0xffffu, 6);
+            f(i + 7, v.w >> 16, 7);
+            i += 8;
+        }
+    }
+#pragma unroll 1
+    for (; i < end; i++) f(i, (uint32_t)idx[i], 8);
+}
+
+// D1': the permutation each chunk applies to list positions (select replay on the identity list).
+__global__ void __launch_bounds__(D3_CT, 2)
+    mtfd3_perm_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t sigma,
+                      uint16_t *__restrict__ perm, uint32_t *__restrict__ err) {
+    extern __shared__ __align__(16) unsigned char d3_raw[];
+    D3Smem &M = *reinterpret_cast<D3Smem *>(d3_raw);
+    d3_fill_lut(M.sel8);
+    __syncthreads();
+    const uint64_t k = (uint64_t)blockIdx.x * D3_CT + threadIdx.x;
+    if (k >= nchunks) return;
+    D3State S{&M.st[threadIdx.x], M.sel8};
+    d3::Regs R;
+    d3::init(S, R, sigma);
+    // entry of slot s = its initial list position sigma - 1 - s; position 256 (sigma == 257, slot 0) is the special one
+    for (uint32_t w4 = 0; 4 * w4 < sigma; w4++) {
+        uint32_t word = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 4; q++) word |= ((sigma - 1u - (4u * w4 + q)) & 0xffu) << (8 * q);
+        S.st[w4 * D3_CT] = word;
+    }
+    if (sigma == 257) R.special = 0;
+    const uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+    bool bad = false;
+    d3_walk(idx, beg, end, (reinterpret_cast<uintptr_t>(idx) & 15) == 0, [&](uint64_t, uint32_t r, int) {
+        if (r >= sigma) bad = true, r = 0;
+        d3::take(S, R, r);
+    });
+    if (bad) atomicMax(err, 1u);
+    // the list front to back -> one row of 16-bit entries, eight per store (what lies behind entry sigma - 1 is row
+    // padding, never read)
+    uint16_t *row = perm + k * D3_STRIDE;
+    int w = d3::WORDS;
+    uint32_t x = 0;
+    auto next = [&]() -> uint32_t {
+        while (!x && w > 0) x = S.bm_load((uint32_t)--w);
+        if (!x) return 0u;
+        const uint32_t bit = 31u - (uint32_t)__clz((int)x);
+        x ^= 1u << bit;
+        const uint32_t slot = 32u * (uint32_t)w + bit;
+        return slot == R.special ? 256u : S.sym_load(slot);
+    };
+    for (uint32_t j0 = 0; j0 < sigma; j0 += 8) {
+        uint32_t e[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) e[q] = next();
+        *reinterpret_cast<uint4 *>(row + j0) =
+            make_uint4(e[0] | (e[1] << 16), e[2] | (e[3] << 16), e[4] | (e[5] << 16), e[6] | (e[7] << 16));
+    }
+}
+
+// D3': replay with the real symbols.  The list at the start of the CTA's tile (super-tile prefix . tiles before) is
+// composed once per CTA into shared memory; a thread's incoming list is that list permuted by its row of `part`.
+__global__ void __launch_bounds__(D3_CT, 2)
+    mtfd3_replay_kernel(const uint16_t *__restrict__ idx, uint64_t N, uint32_t L, uint64_t nchunks, uint32_t G,
+                        uint32_t sigma, const uint16_t *__restrict__ part, const uint16_t *__restrict__ part2,
+                        const int16_t *__restrict__ superprefix, int16_t *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char d3_raw[];
+    D3Smem &M = *reinterpret_cast<D3Smem *>(d3_raw);
+    d3_fill_lut(M.sel8);
+    const uint64_t ntiles = (nchunks + G - 1) / G;
+    for (uint32_t tl = 0; tl < (uint32_t)(D3_CT / D3_G); tl++) { // G == D3_G: the CTA spans D3_CT / D3_G tiles
+        const uint64_t tile = (uint64_t)blockIdx.x * (D3_CT / D3_G) + tl;
+        if (tile >= ntiles) break;
+        const int16_t *sp = superprefix + (tile / G) * sigma;
+        const uint16_t *p2 = part2 + tile * sigma;
+        for (uint32_t j = threadIdx.x; j < sigma; j += D3_CT) M.q[tl][j] = sp[p2[j]];
+    }
+    __syncthreads();
+    const uint64_t k = (uint64_t)blockIdx.x * D3_CT + threadIdx.x;
+    if (k >= nchunks) return;
+    D3State S{&M.st[threadIdx.x], M.sel8};
+    d3::Regs R;
+    d3::init(S, R, sigma);
+    const uint16_t *pp = part + k * D3_STRIDE;
+    for (uint32_t j0 = 0; j0 < sigma; j0 += 8) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(pp + j0);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (uint32_t q = 0; q < 8; q++) {
+            const uint32_t j = j0 + q;
+            if (j < sigma) {
+                const int e = M.q[threadIdx.x / D3_G][(wv[q >> 1] >> (16 * (q & 1))) & 0xffffu];
+                const uint32_t slot = sigma - 1u - j;
+                if (e < 0) R.special = slot;
+                S.sym_store(slot, (uint32_t)e & 0xffu);
+            }
+        }
+    }
+    const uint64_t beg = k * L, end = beg + L < N ? beg + L : N;
+    const bool wide = ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    d3_walk(idx, beg, end, wide, [&](uint64_t i, uint32_t r, int q) {
+        if (r >= sigma) r = 0;
+        const uint32_t id = d3::take(S, R, r);
+        const uint32_t sym16 = id == 256u ? 0xffffu : id; // Nothing = -1
+        switch (q) { // q is a constant at every call site
+        case 0: o0 = sym16; break;
+        case 1: o0 |= sym16 << 16; break;
+        case 2: o1 = sym16; break;
+        case 3: o1 |= sym16 << 16; break;
+        case 4: o2 = sym16; break;
+        case 5: o2 |= sym16 << 16; break;
+        case 6: o3 = sym16; break;
+        case 7:
+            o3 |= sym16 << 16;
+            *reinterpret_cast<uint4 *>(out + (i - 7u)) = make_uint4(o0, o1, o2, o3);
+            break;
+        default: out[i] = (int16_t)sym16; break;
+        }
+    });
 }
 
 // The final list (ranks) comes back through the pinned scalars.  In the composed helpers
@@ -1992,6 +2204,49 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
         tc_ws_release(ctx, mk);
         return h_err[0] ? TC_E_INDEX : TC_OK;
     }
+    if (!ctx->mtfd_v1) {
+        // select-based replay (mtfd3_*): whole waves of resident CTAs (2 per SM), chunks of at most 224 symbols
+        const uint64_t resident = (uint64_t)ctx->sm_count * 2 * D3_CT;
+        const uint64_t waves = std::max<uint64_t>(1, ceil_div_u64(N, resident * d3::LMAX));
+        uint64_t Lw = ceil_div_u64(N, waves * resident);
+        Lw = (Lw + 15) / 16 * 16;
+        const uint32_t L = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(Lw, 32), d3::LMAX);
+        const uint64_t nchunks = ceil_div_u64(N, L);
+        const uint32_t G = D3_G;
+        const uint64_t ntiles = ceil_div_u64(nchunks, G), nsuper = ceil_div_u64(ntiles, G);
+        uint16_t *perm, *part, *tilesum, *part2, *supersum;
+        int16_t *superprefix;
+        uint32_t *d_err;
+        TC_TRY(ws_alloc(ctx, nchunks * D3_STRIDE + 8, &perm));
+        TC_TRY(ws_alloc(ctx, nchunks * D3_STRIDE + 8, &part));
+        TC_TRY(ws_alloc(ctx, ntiles * sigma, &tilesum));
+        TC_TRY(ws_alloc(ctx, ntiles * sigma, &part2));
+        TC_TRY(ws_alloc(ctx, nsuper * sigma, &supersum));
+        TC_TRY(ws_alloc(ctx, nsuper * sigma, &superprefix));
+        TC_TRY(ws_alloc(ctx, 1, &d_err));
+        TC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream));
+        if (!(ctx->attr_done & 16u)) {
+            TC_CUDA(cudaFuncSetAttribute(mtfd3_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D3Smem)));
+            TC_CUDA(cudaFuncSetAttribute(mtfd3_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(D3Smem)));
+            ctx->attr_done |= 16u;
+        }
+        const unsigned cgrid = (unsigned)ceil_div_u64(nchunks, D3_CT);
+        ctx->prof_bytes_next = 2 * N;
+        TC_LAUNCH(ctx, mtfd3_perm_kernel, cgrid, D3_CT, sizeof(D3Smem), d_idx, N, L, nchunks, sigma, perm, d_err);
+        TC_LAUNCH(ctx, mtfd_tile_chain_kernel, (unsigned)ceil_div_u64(ntiles, 4), 128, 0, perm, nchunks, G, sigma, part,
+                  tilesum, ntiles, (uint32_t)D3_STRIDE, (uint32_t)D3_STRIDE);
+        TC_LAUNCH(ctx, mtfd_tile_chain_kernel, (unsigned)ceil_div_u64(nsuper, 4), 128, 0, tilesum, ntiles, G, sigma, part2,
+                  supersum, nsuper, sigma, sigma);
+        TC_LAUNCH(ctx, mtfd_top_chain_kernel, 1, 32, 0, supersum, nsuper, sigma, l0, superprefix);
+        ctx->prof_bytes_next = 4 * N;
+        TC_LAUNCH(ctx, mtfd3_replay_kernel, cgrid, D3_CT, sizeof(D3Smem), d_idx, N, L, nchunks, G, sigma, part, part2,
+                  superprefix, d_sym);
+        uint32_t *h_err = (uint32_t *)ctx->h_scal;
+        TC_TRY(tc_d2h_small(ctx, h_err, d_err, sizeof(uint32_t)));
+        TC_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_ws_release(ctx, mk);
+        return h_err[0] ? TC_E_INDEX : TC_OK;
+    }
     // ~512 chunks per SM keep the 12 resident warps per SM (516 B of list per thread) busy
     uint64_t Lw = ceil_div_u64(N, (uint64_t)ctx->sm_count * 512);
     Lw = (Lw + 15) / 16 * 16;
@@ -2017,9 +2272,9 @@ int mtf_decode_dev_impl(tc_ctx *ctx, const uint16_t *d_idx, uint64_t N, const in
     size_t smem = (size_t)LASTW * T * sizeof(uint32_t);
     TC_LAUNCH(ctx, mtfd_perm_kernel, cgrid, T, smem, d_idx, N, L, nchunks, sigma, perm, d_err);
     TC_LAUNCH(ctx, mtfd_tile_chain_kernel, (unsigned)ceil_div_u64(ntiles, 4), 128, 0, perm, nchunks, G, sigma, part,
-              tilesum, ntiles);
+              tilesum, ntiles, sigma, sigma);
     TC_LAUNCH(ctx, mtfd_tile_chain_kernel, (unsigned)ceil_div_u64(nsuper, 4), 128, 0, tilesum, ntiles, G, sigma, part2,
-              supersum, nsuper);
+              supersum, nsuper, sigma, sigma);
     TC_LAUNCH(ctx, mtfd_top_chain_kernel, 1, 32, 0, supersum, nsuper, sigma, l0, superprefix);
     TC_LAUNCH(ctx, mtfd_replay_kernel, cgrid, T, smem, d_idx, N, L, nchunks, G, sigma, part, part2, superprefix, d_sym);
     uint32_t *h_err = (uint32_t *)ctx->h_scal;
