@@ -248,6 +248,20 @@ def test_abi_layout_c99():
                                os.path.join(ROOT, "tests", "c", "abi_layout.c"), "-o", os.path.join(d, "abi.o")])
 
 
+def test_mtf_decode_step_on_cpu():
+    """tests/c/mtfd_select_test.cpp: the select-based MTF decode step the kernels run
+    (text_compression_b200/csrc/mtfd_select.cuh, one source for host and device) on plain arrays against a list
+    shifted by hand: 4000 chunks, alphabets of 9..257 entries, uniform / small / zero / always-the-back indices."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "mtfd_select_test")
+        subprocess.check_call(["g++", "-O2", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "text_compression_b200", "csrc"),
+                               "-x", "c++", os.path.join(ROOT, "tests", "c", "mtfd_select_test.cpp"), "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
 _HS2C = {"CInt": "i32", "Word32": "i32", "Int32": "i32", "Word64": "i64", "Int64": "i64", "CSize": "i64",
          "CString": "ptr"}
 

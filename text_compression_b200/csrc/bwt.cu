@@ -205,31 +205,59 @@ __global__ void inv_jump_kernel(const uint2 *__restrict__ a, uint64_t S, uint2 *
 }
 // All pointer-jumping rounds in one cooperative launch (a grid barrier between rounds instead of ~20 launches of
 // ~10 us each).  The result of `rounds` rounds is in (rounds odd ? b : a).
+constexpr int JP_PER = 8;  // elements per thread and round, their loads issued together
+constexpr int JP_HOPS = 1; // dependent jumps per round (3 hops and half the rounds measured slower: the rounds are bound by L2 sector reads, not by the barrier)
 __global__ void __launch_bounds__(512)
     inv_jump_all_kernel(uint2 *a, uint2 *b, uint64_t S, int rounds) {
     cg::grid_group grid = cg::this_grid();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int r = 0; r < rounds; r++) {
         const uint2 *src = (r & 1) ? b : a;
         uint2 *dst = (r & 1) ? a : b;
-        for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += stride) {
-            uint2 v = __ldcg(&src[s]); // written by other SMs in the round before: L2, not L1
-            if (v.x != NIL) {
-                const uint2 u = __ldcg(&src[v.x]);
-                v.y += u.y;
-                v.x = u.x;
+        for (uint64_t s0 = t0; s0 < S; s0 += stride * JP_PER) {
+            uint2 v[JP_PER], u[JP_PER];
+#pragma unroll
+            for (int q = 0; q < JP_PER; q++) { // written by other SMs in the round before: L2, not L1
+                const uint64_t s = s0 + q * stride;
+                v[q] = s < S ? __ldcg(&src[s]) : make_uint2(NIL, 0);
             }
-            dst[s] = v;
+#pragma unroll
+            for (int hop = 0; hop < JP_HOPS; hop++) { // every hop reads the round's input array only: reach x (JP_HOPS + 1) per round
+#pragma unroll
+                for (int q = 0; q < JP_PER; q++) u[q] = v[q].x != NIL ? __ldcg(&src[v[q].x]) : make_uint2(NIL, 0);
+#pragma unroll
+                for (int q = 0; q < JP_PER; q++)
+                    if (v[q].x != NIL) v[q] = make_uint2(u[q].x, v[q].y + u[q].y);
+            }
+#pragma unroll
+            for (int q = 0; q < JP_PER; q++) {
+                const uint64_t s = s0 + q * stride;
+                if (s < S) dst[s] = v[q];
+            }
         }
         grid.sync();
     }
 }
-// Text positions -> rows: every splitter on the cycle through row 0 walks its segment and files the rows it passes
-// under their text position.  Walk lengths are geometric, so lanes idle while the longest walk of their warp
-// finishes: this loop is therefore kept to a load, a store and a test, and the per-position work (which symbol owns
-// the row) is done afterwards by inv_text_kernel, one position per thread, without divergence.
-__global__ void inv_rows_kernel(const uint32_t *__restrict__ psi, uint64_t S, uint32_t K,
-                                const uint2 *__restrict__ link, uint32_t *__restrict__ row_at, uint64_t N) {
+// Second walk: every splitter on the cycle through row 0 walks its segment again and writes the text.  Walk lengths
+// are geometric, so lanes idle while the longest walk of their warp finishes and every instruction in this loop costs
+// ~4x: text[i] = F[row] (the code whose row range contains the row) is therefore a lookup in a bucket table over the
+// row's high bits (built on the host with the C table) followed by a binary search between the bucket's two ends
+// (usually zero or one step) instead of nine steps over the whole C table.
+constexpr int IT_BUCKETS = 1024;
+struct FTable {
+    uint16_t bt[IT_BUCKETS + 2]; // bt[k] = largest code index whose first row is <= k << sh
+    int sh;
+};
+__global__ void __launch_bounds__(128)
+    inv_walk2_kernel(const uint32_t *__restrict__ psi, uint64_t S, uint32_t K, const uint2 *__restrict__ link,
+                     CStart cs, FTable ft, uint8_t *__restrict__ text, uint64_t cap, uint64_t N,
+                     uint32_t *__restrict__ err) {
+    __shared__ uint32_t sc[258];
+    __shared__ uint16_t bt[IT_BUCKETS + 2];
+    for (int j = threadIdx.x; j < 258; j += blockDim.x) sc[j] = cs.c[j];
+    for (int j = threadIdx.x; j < IT_BUCKETS + 2; j += blockDim.x) bt[j] = ft.bt[j];
+    __syncthreads();
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const uint2 me = link[s];
@@ -238,50 +266,22 @@ __global__ void inv_rows_kernel(const uint32_t *__restrict__ psi, uint64_t S, ui
     uint64_t g = total - me.y;
     uint32_t cur = (uint32_t)(s * K);
     uint64_t guard = 0;
-    do {
-        if (g >= 1 && g - 1 < N) row_at[g - 1] = cur;
-        cur = psi[cur];
-        g++;
-    } while ((cur & (K - 1)) != 0 && guard++ <= N);
-}
-// text[i] = F[row_at[i]]: the code whose row range contains the row; bucket table over the row's high bits, then
-// a binary search between the bucket's two ends (usually zero or one step).
-constexpr int IT_BUCKETS = 1024;
-__global__ void __launch_bounds__(256)
-    inv_text_kernel(const uint32_t *__restrict__ row_at, const uint2 *__restrict__ link, CStart cs, int sh,
-                    uint8_t *__restrict__ text, uint64_t cap, uint32_t *__restrict__ err) {
-    __shared__ uint32_t sc[258];
-    __shared__ uint16_t bt[IT_BUCKETS + 1];
-    for (int j = threadIdx.x; j < 258; j += blockDim.x) sc[j] = cs.c[j];
-    __syncthreads();
-    for (int bkt = threadIdx.x; bkt <= IT_BUCKETS; bkt += blockDim.x) {
-        const uint64_t x = (uint64_t)bkt << sh; // largest code index whose start is <= x (256 once x is past the rows)
-        int lo = 0, hi = 257;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if ((uint64_t)sc[mid] <= x) lo = mid; else hi = mid;
-        }
-        bt[bkt] = (uint16_t)lo;
-    }
-    __syncthreads();
-    const uint64_t total = link[0].y; // rows on the cycle through row 0, the sentinel's included
-    const uint64_t n_out = total ? total - 1 : 0;
     bool bad = false;
-    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n_out; i += (uint64_t)gridDim.x * blockDim.x * 4) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (i + q >= n_out) break;
-            const uint32_t cur = row_at[i + q];
-            const uint32_t bkt = cur >> sh;
-            int lo = bt[bkt], hi = bt[bkt + 1] + 1;
+    do {
+        const uint32_t nxt = psi[cur]; // the next hop does not wait for this row's symbol
+        if (g >= 1) {
+            const uint32_t bkt = cur >> ft.sh;
+            int lo = bt[bkt], hi = bt[bkt + 1] + 1; // sc[lo] <= cur < sc[hi]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (sc[mid] <= cur) lo = mid; else hi = mid;
             }
             if (lo == 0) bad = true; // fromJust Nothing (src/Data/BWT/Internal.hs:195)
-            else if (i + q < cap) text[i + q] = (uint8_t)(lo - 1);
+            else if (g - 1 < cap) text[g - 1] = (uint8_t)(lo - 1);
         }
-    }
+        cur = nxt;
+        g++;
+    } while ((cur & (K - 1)) != 0 && guard++ <= N);
     if (bad) atomicMax(err, 1u);
 }
 
@@ -321,10 +321,8 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
     const uint32_t K = 16;
     const uint64_t S = ceil_div_u64(N, K);
     uint2 *linkA, *linkB;
-    uint32_t *row_at;
     TC_TRY(ws_alloc(ctx, S, &linkA));
     TC_TRY(ws_alloc(ctx, S, &linkB));
-    TC_TRY(ws_alloc(ctx, N, &row_at));
     uint32_t *d_err;
     TC_TRY(ws_alloc(ctx, 1, &d_err));
     TC_CUDA(cudaMemsetAsync(d_err, 0, sizeof(uint32_t), ctx->stream));
@@ -333,6 +331,8 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
     int rounds = 1;
     while ((1ull << rounds) < S) rounds++;
     if (ctx->coop_ok) {
+        rounds = 1;
+        for (uint64_t reach = JP_HOPS + 1; reach < S; reach *= JP_HOPS + 1) rounds++;
         int per_sm = 0;
         TC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inv_jump_all_kernel, 512, 0));
         if (per_sm > 2) per_sm = 2;
@@ -351,12 +351,16 @@ int bwt_decode_impl(tc_ctx *ctx, Src src, uint64_t N, uint8_t *d_text, uint64_t 
             std::swap(linkA, linkB);
         }
     }
-    TC_LAUNCH(ctx, inv_rows_kernel, gridS, 128, 0, psi, S, K, (const uint2 *)linkA, row_at, N);
-    int sh = 0;
-    while (((N - 1) >> sh) >= (uint64_t)IT_BUCKETS) sh++;
+    FTable ft;
+    ft.sh = 0;
+    while (((N - 1) >> ft.sh) >= (uint64_t)IT_BUCKETS) ft.sh++;
+    for (int k = 0, lo = 0; k < IT_BUCKETS + 2; k++) {
+        const uint64_t x = (uint64_t)k << ft.sh;
+        while (lo < 256 && (uint64_t)cs.c[lo + 1] <= x) lo++; // largest index with cs.c[index] <= x, at most 256
+        ft.bt[k] = (uint16_t)lo;
+    }
     ctx->prof_bytes_next = 5 * N;
-    TC_LAUNCH(ctx, inv_text_kernel, (unsigned)std::min<uint64_t>(ceil_div_u64(N, 256 * 4 * 4), 1u << 20), 256, 0,
-              (const uint32_t *)row_at, (const uint2 *)linkA, cs, sh, d_text, cap, d_err);
+    TC_LAUNCH(ctx, inv_walk2_kernel, gridS, 128, 0, psi, S, K, (const uint2 *)linkA, cs, ft, d_text, cap, N, d_err);
     TC_TRY(tc_d2h_small(ctx, h, &linkA[0].y, sizeof(uint32_t)));
     TC_TRY(tc_d2h_small(ctx, h + 1, d_err, sizeof(uint32_t)));
     TC_CUDA(cudaStreamSynchronize(ctx->stream));
