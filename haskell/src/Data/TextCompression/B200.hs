@@ -41,6 +41,7 @@ module Data.TextCompression.B200
   , compressBlocksPackedW8
   , unpackBlockW8
   , decodePackedW8
+  , decodeBlocksPackedW8
     -- * Data.FMIndex.Internal replacements
   , B200FM
   , buildFMIndexW8
@@ -65,12 +66,12 @@ import qualified Data.Sequence         as DS
 import           Data.Word             (Word16, Word32, Word64, Word8)
 import           Foreign.C.String      (CString, peekCString)
 import           Foreign.C.Types       (CInt (..), CSize (..))
-import           Foreign.ForeignPtr    (ForeignPtr, newForeignPtr, withForeignPtr)
+import           Foreign.ForeignPtr    (ForeignPtr, newForeignPtr, touchForeignPtr, withForeignPtr)
 import           Foreign.Marshal.Alloc (alloca)
-import           Foreign.Marshal.Array (peekArray, pokeArray, withArray)
-import           Foreign.Marshal.Utils (withMany)
+import           Foreign.Marshal.Array (allocaArray, peekArray, pokeArray, withArray)
+import           Foreign.Marshal.Utils (copyBytes, withMany)
 import           Foreign.Ptr           (FunPtr, Ptr, castPtr, nullPtr)
-import           Foreign.Storable      (peek, peekByteOff)
+import           Foreign.Storable      (peek, peekByteOff, peekElemOff, pokeElemOff)
 import           System.Environment   (lookupEnv)
 import           System.IO.Unsafe      (unsafePerformIO)
 
@@ -124,6 +125,9 @@ foreign import ccall unsafe "tc_packed_unpack"
   c_packed_unpack :: Ptr Word8 -> Word64 -> Ptr Word32 -> Ptr Int16 -> Word64 -> Ptr () -> IO CInt
 foreign import ccall safe "tc_packed_decode"
   c_packed_decode :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Ptr Word8 -> Word64 -> Ptr Word64 -> IO CInt
+foreign import ccall safe "tc_blocks_decode_packed"
+  c_blocks_decode_packed :: Ptr TcCtx -> Word64 -> Ptr (Ptr Word8) -> Ptr Word64 -> Ptr (Ptr Word8) -> Ptr Word64
+                         -> Ptr Word64 -> IO CInt
 foreign import ccall safe "tc_fm_build"
   c_fm_build :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Word32 -> Ptr (Ptr TcFm) -> IO CInt
 foreign import ccall safe "&tc_fm_free" p_fm_free :: FunPtr (Ptr TcFm -> IO ())
@@ -366,6 +370,33 @@ decodePackedW8 blob = unsafePerformIO $ withB200 $ \ctx ->
       c_packed_decode ctx (castPtr p) (fromIntegral len) po (fromIntegral (n + 2)) pn >>= check ctx
       m <- fromIntegral <$> peek pn
       BS.packCStringLen (castPtr po, m)
+
+-- | Multi-block decompression (tc_blocks_decode_packed): several containers in flight on the device.
+decodeBlocksPackedW8 :: [BS.ByteString] -> [BS.ByteString]
+decodeBlocksPackedW8 []    = []
+decodeBlocksPackedW8 blobs = unsafePerformIO $ withB200 $ \ctx -> do
+  let nb = length blobs
+  ns <- forM blobs $ \b -> BSU.unsafeUseAsCStringLen b $ \(p, len) ->
+          if len >= 24 then fromIntegral <$> (peekByteOff p 16 :: IO Word64) else pure (0 :: Int)   -- tc_packed_header.n
+  outs <- forM ns $ \n -> pinned (n + 2)
+  ins  <- forM blobs $ \b -> do                      -- containers in pinned memory: the H2D copies run at PCIe rate
+            fp <- pinned (BS.length b)
+            withForeignPtr fp $ \d -> BSU.unsafeUseAsCStringLen b $ \(p, len) -> copyBytes d (castPtr p) len
+            pure fp
+  allocaArray nb $ \pblob -> allocaArray nb $ \pbytes -> allocaArray nb $ \ptext ->
+    allocaArray nb $ \pcap -> allocaArray nb $ \pn -> do
+      forM_ (zip3 [0 ..] ins blobs) $ \(i, fp, b) -> withForeignPtr fp $ \d -> do
+        pokeElemOff pblob i d
+        pokeElemOff pbytes i (fromIntegral (BS.length b))
+      forM_ (zip3 [0 ..] outs ns) $ \(i, fp, n) -> withForeignPtr fp $ \d -> do
+        pokeElemOff ptext i d
+        pokeElemOff pcap i (fromIntegral (n + 2))
+      c_blocks_decode_packed ctx (fromIntegral nb) pblob pbytes ptext pcap pn >>= check ctx
+      res <- forM (zip [0 ..] outs) $ \(i, fp) -> do
+        m <- fromIntegral <$> peekElemOff pn i
+        withForeignPtr fp $ \d -> BS.packCStringLen (castPtr d, m)
+      mapM_ touchForeignPtr ins
+      pure res
 
 -- | Device-resident FM-index handle (tc_fm); freed by the GC finaliser.
 newtype B200FM = B200FM (ForeignPtr TcFm)

@@ -175,6 +175,13 @@ int tc_packed_unpack(const void *blob, uint64_t bytes, uint32_t *count, int16_t 
                      tc_block_info *info);
 /* Container -> text on the device (unpack kernel, then the inverse chain below). */
 int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap, uint64_t *n_out);
+/* The same for a list of containers (multi-block decompression, the inverse of tc_blocks_encode_packed): up to
+ * TC_B200_LANES containers are in flight, each on its own context and stream, so the copies and host syncs of one are
+ * covered by the kernels of the others.  n_out[b] is the length of block b; a block longer than cap[b] gives TC_E_CAP
+ * after every block has been decoded (n_out[b] set), any other error stops the batch.  text[b] must be distinct
+ * buffers; all copies have completed when the call returns. */
+int tc_blocks_decode_packed(tc_ctx *ctx, uint64_t nblocks, const void *const *blob, const uint64_t *bytes,
+                            uint8_t *const *text, const uint64_t *cap, uint64_t *n_out);
 
 /* inverses: runs -> (MTF indices ->) BWT -> text. */
 int tc_bwt_rle_decode(tc_ctx *ctx, const uint32_t *count, const int16_t *rsym, uint64_t R, uint8_t *text,

@@ -316,3 +316,40 @@ def test_mtf_decode_kernels_agree(ctx, orc):
         out = np.empty(idx.size, dtype=np.int16)
         assert c.L.tc_mtf_decode(c.h, ptr(idx), idx.size, ptr(fin), fin.size, ptr(out)) == TC_E_INDEX
     ctx1.close()
+
+
+def test_blocks_decode_packed_vs_texts(ctx, orc):
+    """tc_blocks_decode_packed (multi-block decompression, lanes) gives back every block of a ragged batch, both
+    chains, an empty block included; equals the single-container call; a stream round trip goes through it; a
+    malformed container stops the batch with an error."""
+    from text_compression_b200 import block, stream
+    from text_compression_b200._lib import TcError
+    texts = [gen_bytes(3, 1_000_003), gen_acgtn(4, 2_500_000), gen_words(5, 700_001), gen_bytes(6, 0), gen_ascii(7, 1),
+             gen_acgtn(8, 4097), gen_bytes(9, 3 << 20), gen_acgtn(10, 65_536), gen_bytes(11, 4095)]
+    from text_compression_b200._lib import FromJustError
+    for with_mtf in (True, False):
+        blobs = block.compress_blocks_packed(texts, with_mtf, ctx)
+        keep = list(range(len(texts)))
+        if not with_mtf:
+            # reference quirk (SURVEY.md 2.3, Q1-Q3): seqToRLE writes a trailing Nothing twice, so a BWT that ENDS with
+            # its Nothing does not survive BWT -> RLE -> BWT in the reference either: fromBWT meets a second Nothing
+            quirk = [b for b in keep if texts[b].size and int(np.nonzero(orc.bwt_encode(texts[b]) < 0)[0][0]) == texts[b].size]
+            assert 4 in quirk                                   # the one-symbol text: BWT = [x, Nothing]
+            for b in quirk:
+                with pytest.raises(FromJustError):
+                    block.decompress_packed(blobs[b], ctx)
+                with pytest.raises(FromJustError):              # and it stops a batch
+                    block.decompress_blocks_packed([blobs[0], blobs[b], blobs[1]], ctx)
+            keep = [b for b in keep if b not in quirk]
+        got = block.decompress_blocks_packed([blobs[b] for b in keep], ctx)
+        assert len(got) == len(keep)
+        for g, b in zip(got, keep):
+            assert g == texts[b].tobytes(), (with_mtf, b)
+            assert block.decompress_packed(blobs[b], ctx) == g
+    data = np.concatenate(texts).tobytes()
+    assert stream.decompress_stream(stream.compress_stream(data, 1 << 20, ctx=ctx), ctx) == data
+    bad = [np.array(b, copy=True) for b in block.compress_blocks_packed(texts[:4], True, ctx)]
+    bad[1][0] ^= 0xff          # magic
+    with pytest.raises((TcError, ValueError)):
+        block.decompress_blocks_packed(bad, ctx)
+    assert block.decompress_blocks_packed([], ctx) == []

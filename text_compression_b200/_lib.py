@@ -82,6 +82,7 @@ _SIGS = {
     "tc_packed_info": (_int, [_vp, _u64, C.POINTER(BlockInfo), _pu32]),
     "tc_packed_unpack": (_int, [_vp, _u64, _vp, _vp, _u64, C.POINTER(BlockInfo)]),
     "tc_packed_decode": (_int, [_vp, _vp, _u64, _vp, _u64, _pu64]),
+    "tc_blocks_decode_packed": (_int, [_vp, _u64, _vp, _vp, _vp, _vp, _vp]),
     "tc_bwt_rle_decode": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _pu64]),
     "tc_bwt_mtf_rle_decode": (_int, [_vp, _vp, _vp, C.POINTER(BlockInfo), _vp, _u64, _pu64]),
     "tc_bwt_encode_dev": (_int, [_vp, _vp, _u64, _vp, _pu64, _vp]),

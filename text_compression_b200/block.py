@@ -166,3 +166,30 @@ def decompress_packed(blob, ctx=None) -> bytes:
     n_out = C.c_uint64(0)
     ctx.call("tc_packed_decode", ptr(a), a.size, ptr(out), cap, C.byref(n_out))
     return out[: n_out.value].tobytes()
+
+
+def decompress_blocks_packed(blobs, ctx=None) -> list:
+    """tc_blocks_decode_packed: a list of containers -> their texts, several containers in flight on the device
+    (the inverse of compress_blocks_packed).  Reference quirk kept: in the BWT -> RLE chain (with_mtf False) seqToRLE
+    writes a trailing Nothing twice, so a block whose BWT ends with its Nothing raises FromJustError on the way back,
+    as fromBWT does in the reference."""
+    ctx = ctx or default_context()
+    arrs = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b) for b in blobs]
+    nb = len(arrs)
+    if nb == 0:
+        return []
+    caps = []
+    for a in arrs:
+        info = BlockInfo()
+        rc = ctx.L.tc_packed_info(ptr(a), a.size, C.byref(info), None)
+        if rc != TC_OK:
+            _raise(None, rc)
+        caps.append(int(info.n) + 2)
+    outs = [np.empty(c, dtype=np.uint8) for c in caps]
+    bp = (C.c_void_p * nb)(*[a.ctypes.data for a in arrs])
+    by = (C.c_uint64 * nb)(*[a.size for a in arrs])
+    op = (C.c_void_p * nb)(*[o.ctypes.data for o in outs])
+    cp = (C.c_uint64 * nb)(*caps)
+    n_out = (C.c_uint64 * nb)()
+    ctx.call("tc_blocks_decode_packed", nb, bp, by, op, cp, n_out)
+    return [outs[b][: int(n_out[b])].tobytes() for b in range(nb)]

@@ -759,10 +759,9 @@ extern "C" int tc_blocks_encode_dev(tc_ctx *ctx, uint64_t nblocks, const uint8_t
     });
 }
 
-extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap,
-                                uint64_t *n_out) {
-    TC_ENTER(ctx);
-    if (!n_out) return TC_E_ARG;
+namespace {
+// container (host) -> text (host) on one context; the scratch it takes is released again
+int packed_decode_one(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap, uint64_t *n_out) {
     *n_out = 0;
     tc_packed_header h;
     TC_TRY(packed_check(blob, bytes, &h));
@@ -774,6 +773,7 @@ extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, u
     uint32_t *d_count;
     int16_t *d_rsym;
     const uint64_t pay = h.total_bytes - h.off_cnt4;
+    WsMark mk = tc_ws_mark(ctx);
     TC_TRY(ws_alloc(ctx, pay, &d_blob));
     TC_TRY(ws_alloc(ctx, h.R, &d_count));
     TC_TRY(ws_alloc(ctx, h.R, &d_rsym));
@@ -782,5 +782,45 @@ extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, u
     TC_TRY(rle_unpack_dev_impl(ctx, d_blob, d_blob + (h.off_sym8 - o0), (const uint32_t *)(d_blob + (h.off_hi - o0)),
                                (const uint64_t *)(d_blob + (h.off_big_idx - o0)),
                                (const uint32_t *)(d_blob + (h.off_big_cnt - o0)), h.n_big, h.R, d_count, d_rsym));
-    return decode_runs_dev(ctx, d_count, d_rsym, h.R, (h.flags & TC_PACKED_MTF) != 0, &info, text, cap, n_out);
+    int rc = decode_runs_dev(ctx, d_count, d_rsym, h.R, (h.flags & TC_PACKED_MTF) != 0, &info, text, cap, n_out);
+    tc_ws_release(ctx, mk);
+    return rc;
+}
+} // namespace
+
+extern "C" int tc_packed_decode(tc_ctx *ctx, const void *blob, uint64_t bytes, uint8_t *text, uint64_t cap,
+                                uint64_t *n_out) {
+    TC_ENTER(ctx);
+    if (!n_out) return TC_E_ARG;
+    return packed_decode_one(ctx, blob, bytes, text, cap, n_out);
+}
+
+// Multi-block decompression: the lanes of tc_blocks_encode_packed, each taking the next unclaimed container and
+// running copy in -> unpack -> RLE -> MTF -> BWT inverse -> copy out on its own context and stream, so one lane's copies
+// and host syncs are covered by the other lanes' kernels.
+extern "C" int tc_blocks_decode_packed(tc_ctx *ctx, uint64_t nblocks, const void *const *blob, const uint64_t *bytes,
+                                       uint8_t *const *text, const uint64_t *cap, uint64_t *n_out) {
+    if (!ctx) return TC_E_ARG;
+    if (nblocks == 0) return TC_OK;
+    if (!blob || !bytes || !text || !cap || !n_out) return TC_E_ARG;
+    for (uint64_t b = 0; b < nblocks; b++) n_out[b] = 0;
+    std::atomic<uint64_t> next{0};
+    return run_lanes(ctx, nblocks, [&](tc_ctx *c) -> int {
+        if (cudaSetDevice(c->device) != cudaSuccess) return TC_E_CUDA; // helper threads start on device 0
+        TC_TRY(tc_ws_reset(c));
+        DrainGuard drain{c};
+        int rc_all = TC_OK;
+        for (uint64_t b = next.fetch_add(1); b < nblocks; b = next.fetch_add(1)) {
+            int rc = packed_decode_one(c, blob[b], bytes[b], text[b], cap[b], &n_out[b]);
+            if (rc == TC_E_CAP) {
+                rc_all = TC_E_CAP;
+                continue;
+            }
+            if (rc != TC_OK) {
+                next.store(nblocks); // the other lanes stop at their next block
+                return rc;
+            }
+        }
+        return rc_all;
+    });
 }

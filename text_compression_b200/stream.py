@@ -57,9 +57,9 @@ def split_stream(blob):
 
 
 def decompress_stream(blob, ctx=None) -> bytes:
-    """TCZ1 stream -> bytes (every container decoded on the device: tc_packed_decode)."""
+    """TCZ1 stream -> bytes (all containers through one tc_blocks_decode_packed call: several blocks in flight)."""
     _, total, parts = split_stream(blob)
-    out = b"".join(block.decompress_packed(np.frombuffer(p, dtype=np.uint8), ctx) for p in parts)
+    out = b"".join(block.decompress_blocks_packed([np.frombuffer(p, dtype=np.uint8) for p in parts], ctx))
     if len(out) != total:
         raise ValueError(f"TCZ1: decoded {len(out)} bytes, header says {total}")
     return out
