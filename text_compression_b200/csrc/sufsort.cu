@@ -338,14 +338,19 @@ constexpr int PT_ITEMS = 8;
 constexpr int PT_TILE = PT_T * PT_ITEMS;
 constexpr int PT_WARPS = PT_T / 32;
 
-// one CTA: segment starts from the level-1 histogram, + tile and chunk tables for level 2
+// one CTA: segment starts from the level-1 histogram, + tile and chunk tables for level 2.  hist1 == nullptr: the
+// histogram comes by value (raw-byte keys: the level-1 digit is the suffix's first byte, so the level-1 histogram
+// is the byte histogram the host already holds).
+struct Hist256 {
+    uint32_t c[256];
+};
 __global__ void __launch_bounds__(256)
-    seg_tables_kernel(const uint32_t *__restrict__ hist1, int nseg, uint32_t *__restrict__ segstart /*nseg+1*/,
+    seg_tables_kernel(const uint32_t *__restrict__ hist1, Hist256 hv, int nseg, uint32_t *__restrict__ segstart /*nseg+1*/,
                       uint32_t *__restrict__ cursor1, uint32_t *__restrict__ tilebase /*nseg+1*/,
                       uint32_t *__restrict__ chunkbase /*nseg+1*/) {
     __shared__ uint32_t sh[256 / 32 + 1];
     const int s = threadIdx.x;
-    uint32_t c = s < nseg ? hist1[s] : 0;
+    uint32_t c = s < nseg ? (hist1 ? hist1[s] : hv.c[s]) : 0;
     uint32_t tot;
     uint32_t ex = block_excl_sum<uint32_t, 256>(c, sh, &tot);
     if (s < nseg) {
@@ -446,7 +451,18 @@ struct PtSmem {
 // in radix.cu), records staged in digit order, then written as runs; the tile's slice of every
 // bucket is reserved with one atomicAdd on the bucket cursor (placement inside a bucket need
 // not be deterministic -- the final sort orders it).
-// FIRST: the input is ukey[i]; the record becomes (ukey, i | T[i-1] << 24) when packprev.
+// FIRST: the input is ukey[i] -- or, with ukey_in == nullptr, the raw-byte key read straight from the text (big-endian
+// text[i .. i+3], zeros past the end: uk_keys_raw_kernel's key without a pass of its own); the record becomes
+// (ukey, i | T[i-1] << 24) when packprev.
+__device__ __forceinline__ uint32_t raw_key_at(const uint8_t *__restrict__ t, uint32_t i, uint32_t n, bool aligned) {
+    if (aligned && i + 8 <= n) { // both words inside the text
+        const uint32_t *t32 = reinterpret_cast<const uint32_t *>(t);
+        return __byte_perm(t32[i >> 2], t32[(i >> 2) + 1], 0x0123u + 0x1111u * (i & 3u));
+    }
+    uint32_t u = 0;
+    for (int k = 0; k < 4; k++) u = (u << 8) | (i + k < n ? (uint32_t)t[i + k] : 0u);
+    return u;
+}
 template <bool FIRST>
 __global__ void __launch_bounds__(PT_T, 6)
     part_kernel(const uint32_t *__restrict__ ukey_in, const uint8_t *__restrict__ text, int packprev,
@@ -478,7 +494,11 @@ __global__ void __launch_bounds__(PT_T, 6)
     for (int r = 0; r < PT_ITEMS; r++) {
         uint32_t j = w * (32 * PT_ITEMS) + r * 32 + lane;
         key[r] = 0;
-        if (j < cnt) key[r] = FIRST ? ukey_in[beg + j] : rec_in[beg + j].x;
+        if (j < cnt) {
+            if (!FIRST) key[r] = rec_in[beg + j].x;
+            else if (ukey_in) key[r] = ukey_in[beg + j];
+            else key[r] = raw_key_at(text, beg + j, (uint32_t)n, (reinterpret_cast<uintptr_t>(text) & 3) == 0);
+        }
     }
 #pragma unroll
     for (int r = 0; r < PT_ITEMS; r++) {
@@ -964,7 +984,13 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
         bool flat = sigma == 256 && !ctx->no_rawkey;
         for (int c = 0; c < 256 && flat; c++) flat = fabs((double)hist[c] * 256.0 / (double)n - 1.0) < 0.05;
         ctx->prof_bytes_next = n + 4 * n;
-        if (flat) {
+        const bool raw_direct = flat && B1 == 8 && nb1 == 256; // level-1 digit = first byte: no key pass at all
+        Hist256 hv;
+        memcpy(hv.c, hist, sizeof hv.c);
+        if (raw_direct) {
+            ukey = nullptr;
+            ctx->prof_bytes_next = 0;
+        } else if (flat) {
             TC_CUDA(cudaFuncSetAttribute(uk_keys_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
             TC_LAUNCH(ctx, uk_keys_raw_kernel, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, d_text, (uint32_t)n,
                       B1 ? 32 - B1 : 31, ukey, hist1);
@@ -974,7 +1000,8 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
             TC_LAUNCH_AS(ctx, "uk_keys_kernel", kkeys, (unsigned)ceil_div_u64(n, PC_TILE), PC_T, PC_SMEM, pw, b, kb, gb, G, uk_lut,
                          (uint32_t)n, B1 ? 32 - B1 : 31, ukey, hist1);
         }
-        TC_LAUNCH(ctx, seg_tables_kernel, 1, 256, 0, hist1, nb1, segstart, cursor1, tilebase, chunkbase);
+        TC_LAUNCH(ctx, seg_tables_kernel, 1, 256, 0, raw_direct ? (const uint32_t *)nullptr : (const uint32_t *)hist1, hv, nb1,
+                  segstart, cursor1, tilebase, chunkbase);
         ctx->prof_bytes_next = 4 * n + (packprev ? n : 0) + 8 * n;
         TC_LAUNCH(ctx, part_kernel<true>, (unsigned)ceil_div_u64(n, PT_TILE), PT_T, sizeof(PtSmem), ukey, d_text, packprev,
                   (const uint2 *)nullptr, recA, n, 32 - B1, (uint32_t)(nb1 - 1), (const uint32_t *)nullptr,
