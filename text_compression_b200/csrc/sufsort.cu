@@ -700,6 +700,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 5)
     __shared__ FsWarp fs[FS_WARPS];
     FsWarp &W = fs[threadIdx.x >> 5];
     const unsigned lane = lane_id();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { // the empty suffix sorts first (row 0); its BWT symbol is the last text symbol
+        sa[0] = (uint32_t)n;
+        if (bwt) bwt[0] = text[n - 1];
+    }
     const uint32_t bk = blockIdx.x * FS_WARPS + (threadIdx.x >> 5);
     if (bk >= nbuckets) return;
     const uint32_t s = starts[bk], M = starts[bk + 1] - s;
@@ -751,14 +755,6 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 5)
             bwt[1 + s + j] = c;
             if (idx == 0) *primary = 1ull + s + j;
         }
-    }
-}
-
-__global__ void sa_row0_kernel(const uint8_t *__restrict__ t, uint64_t n, uint32_t *__restrict__ sa,
-                               uint8_t *__restrict__ bwt) {
-    if (threadIdx.x == 0) {
-        sa[0] = (uint32_t)n;
-        if (bwt) bwt[0] = t[n - 1];
     }
 }
 
@@ -1021,8 +1017,6 @@ int tc_suffix_sort_bwt_dev(tc_ctx *ctx, const uint8_t *d_text, uint64_t n, uint3
             recF = recB;
             startsF = starts2;
         }
-        // the empty suffix sorts first (row 0); its BWT symbol is the last text symbol
-        TC_LAUNCH(ctx, sa_row0_kernel, 1, 32, 0, d_text, n, d_sa, d_bwt);
         ctx->prof_bytes_next = 8 * n + 4 * n + (d_bwt ? n : 0);
         TC_LAUNCH(ctx, final_sort_kernel, (unsigned)ceil_div_u64(nbk, FS_WARPS), FS_WARPS * 32, 0, recF, startsF, nbk,
                   32 - PB, pw, b, kb, k, n, packprev, d_text, d_sa, d_bwt, d_primary, flags);
