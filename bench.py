@@ -61,7 +61,7 @@ def ncu_row(kernel: str):
     """{traffic, warp_instructions, issue_active_pct} per launch of `kernel` from the committed
     ncu --set full capture of this workload (profiles/, produced by tools/make_profiles.sh)."""
     import csv
-    path = os.path.join(ROOT, "profiles", f"r2_ncu_full_summary_{ALPHABET}.csv")
+    path = os.path.join(ROOT, "profiles", f"r2c_ncu_full_summary_{ALPHABET}.csv")
     short = kernel.split("<")[0].strip()
     try:
         rows = list(csv.reader(open(path)))
