@@ -346,6 +346,18 @@ def test_blocks_decode_packed_vs_texts(ctx, orc):
         for g, b in zip(got, keep):
             assert g == texts[b].tobytes(), (with_mtf, b)
             assert block.decompress_packed(blobs[b], ctx) == g
+    # the pointer-jumping rounds as separate launches (devices without cooperative launch) give the same text
+    import os
+    from text_compression_b200 import _lib
+    os.environ["TC_B200_NO_COOP"] = "1"
+    try:
+        ctx_nc = _lib.Context(0)
+    finally:
+        del os.environ["TC_B200_NO_COOP"]
+    blobs = block.compress_blocks_packed(texts[:3], True, ctx)
+    for b in range(3):
+        assert block.decompress_packed(blobs[b], ctx_nc) == texts[b].tobytes()
+    ctx_nc.close()
     data = np.concatenate(texts).tobytes()
     assert stream.decompress_stream(stream.compress_stream(data, 1 << 20, ctx=ctx), ctx) == data
     bad = [np.array(b, copy=True) for b in block.compress_blocks_packed(texts[:4], True, ctx)]
