@@ -55,6 +55,28 @@ def gen_words(seed, n, vocab=600, dup_every=1 << 18, dup_len=6000):
     return np.frombuffer(bytes(out[:n]), dtype=np.uint8).copy()
 
 
+def python_corpus(nbytes):
+    """Real, correlated, repetitive text: Python sources of this interpreter's site-packages, concatenated in the
+    order of a sorted top-down walk that STOPS as soon as nbytes have been read (enumerating the whole tree first costs
+    a minute or more on a freshly started box whose image is paged in on demand).  The same image runs here and on
+    the GPU box, so the corpus is the same on both.  Returns fewer bytes if the tree holds less."""
+    import os
+    import sysconfig
+    buf = bytearray()
+    for d, dirs, files in os.walk(sysconfig.get_paths()["purelib"]):
+        dirs.sort()
+        for f in sorted(files):
+            if f.endswith(".py"):
+                try:
+                    with open(os.path.join(d, f), "rb") as fh:
+                        buf += fh.read()
+                except OSError:
+                    pass
+                if len(buf) >= nbytes:
+                    return np.frombuffer(bytes(buf[:nbytes]), dtype=np.uint8)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
 def gen_reads(seed, text, q, m, mut_frac=0.10):
     """q reads of m symbols at uniform offsets; mut_frac of them get one random substitution."""
     r = splitmix64(seed, 3 * q)

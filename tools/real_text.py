@@ -1,21 +1,12 @@
 """Throughput on non-synthetic text: a corpus of Python sources from site-packages (correlated,
-repetitive).  python tools/real_text.py [MiB]"""
+repetitive; tests/util.python_corpus).  python tools/real_text.py [MiB]"""
 import sys, os, time, glob
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from text_compression_b200 import _lib, block
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-import sysconfig
-root = sysconfig.get_paths()["purelib"]
-buf = bytearray()
-for f in sorted(glob.glob(root + "/**/*.py", recursive=True)):
-    try:
-        buf += open(f, "rb").read()
-    except Exception:
-        pass
-    if len(buf) >= mib << 20:
-        break
-text = np.frombuffer(bytes(buf[: mib << 20]), dtype=np.uint8)
+from tests.util import python_corpus
+text = python_corpus(mib << 20)
 print("corpus bytes", text.size, "distinct", len(set(text.tolist()[:1000000])))
 ctx = _lib.Context(0)
 for _ in range(2):
