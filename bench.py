@@ -439,9 +439,9 @@ def run_b200(args):
                                        "reference algorithm, single thread (the reference path is sequential)"},
         }
     if args.decode:
-        dec = run_decode(args, ctx, host_blocks[0], peak)
-        if line is not None:
-            line["decode"] = dec
+        if rank == 0:   # a single-GPU figure: the other ranks would only contend for the host's copy path
+            line["decode"] = run_decode(args, ctx, host_blocks[0], peak)
+        barrier()
     if line is not None and args.c1:
         line["c1_roundtrip"] = run_c1(ctx)
     if args.fm and world >= 1:
