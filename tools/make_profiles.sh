@@ -37,9 +37,9 @@ summ /tmp/prof_lsd.ncu-rep lsd rs_scatter rs_hist sa_keys2 sa_update
 # inverse chain
 python tools/decode_times.py bytes > $OUT/${TAG}_decode_times_bytes.txt || exit 1
 python tools/decode_times.py acgtn > $OUT/${TAG}_decode_times_acgtn.txt || exit 1
-ncu --set full --clock-control none --import-source on -k regex:"inv_|cs_|mtfd_|mtfds_|rle_expand|rle_len" -c 60 -o /tmp/prof_dec -f \
+ncu --set full --clock-control none --import-source on -k regex:"inv_|cs_|mtfd|rle_expand|rle_len" -c 40 -o /tmp/prof_dec -f \
     python tools/decode_times.py bytes > $OUT/${TAG}_ncu_full_decode.log 2>&1
-summ /tmp/prof_dec.ncu-rep decode inv_walk1 inv_jump inv_walk2 cs_scatter mtfd_perm mtfd_replay rle_expand
+summ /tmp/prof_dec.ncu-rep decode inv_walk1 inv_jump_all inv_walk2 cs_scatter mtfd3_perm mtfd3_replay mtfd_tile_chain rle_expand
 # FM-index: 100 Mbp (index mostly L2-resident) and 1 Gbp (1.98 GB image: HBM)
 python tools/fm_step.py 100000000 1000000 200000 > $OUT/${TAG}_fm_step_100M.txt || exit 1
 ncu --set full --clock-control none --import-source on -k regex:"fm_" -c 12 -o /tmp/prof_fm -f \
