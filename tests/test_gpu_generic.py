@@ -121,3 +121,29 @@ def test_sorttb_and_magic_inverse(orc):
     assert generic.magicInverseBWT([("a", 0), ("b", 1)]) == []
     with pytest.raises(FromJustError):
         generic.magicInverseBWT([(None, 1), (None, 0)])
+
+
+def test_generic_fm_index_vs_oracle(orc):
+    """FM-index over words, ints and tuples (rank-compressed on the host): counts and located positions equal the
+    oracle's on the same codes; a pattern with an element the text lacks, and the empty pattern, give Nothing."""
+    from text_compression_b200 import generic
+    rng = np.random.default_rng(11)
+    vocab = ["the", "quick", "brown", "fox", "jumps", "over", "lazy", "dog", "and", "cat"]
+    texts = [[vocab[i] for i in rng.integers(0, len(vocab), size=5000)],
+             rng.integers(-50, 50, size=20000).tolist(),
+             [(int(a), "xy"[int(b)]) for a, b in zip(rng.integers(0, 7, size=3000), rng.integers(0, 2, size=3000))]]
+    for xs in texts:
+        fm = generic.FMIndexG(xs, 4)
+        al = generic.Alphabet(xs)
+        ofm = orc.FMIndex(al.encode(xs))
+        pats = [xs[o:o + m] for o, m in zip(rng.integers(0, len(xs) - 8, size=200).tolist(), rng.integers(1, 6, size=200).tolist())]
+        want_c = [ofm.count(bytes(al.rank[x] for x in p)) for p in pats]
+        got_c = fm.count_many(pats)
+        assert got_c == [None if c < 0 else c for c in want_c]
+        got_l = fm.locate_many(pats[:50])
+        for p, g in zip(pats[:50], got_l):
+            assert g == ofm.locate(bytes(al.rank[x] for x in p)).tolist()
+            for pos in g:
+                assert xs[pos - 1: pos - 1 + len(p)] == p
+        assert fm.count([]) is None and fm.count([xs[0], object]) is None and fm.locate([object]) == []
+        fm.close()

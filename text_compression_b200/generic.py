@@ -24,7 +24,7 @@ import numpy as np
 from ._lib import FromJustError, TC_E_FROMJUST, default_context, ptr
 
 __all__ = ["TooManySymbols", "Alphabet", "toBWT", "fromBWT", "createSuffixArray", "seqToMTF", "seqFromMTF", "seqToRLE",
-           "seqFromRLE", "BWTMatrix", "createBWTMatrix", "sortTB", "magicInverseBWT"]
+           "seqFromRLE", "BWTMatrix", "createBWTMatrix", "sortTB", "magicInverseBWT", "FMIndexG"]
 
 
 class TooManySymbols(ValueError):
@@ -152,6 +152,59 @@ def seqFromRLE(flat, ctx=None) -> list:
     cnt = np.array([max(int(y1.decode() if isinstance(y1, (bytes, bytearray)) else y1), 0) for y1, _ in pairs], dtype=np.uint32)
     s = unrle_codes(RLE(cnt, al.encode_maybe([s for _, s in pairs]), "W"), ctx)
     return al.decode_maybe(s.codes)
+
+
+# ---- Data.FMIndex on any ordered elements ----------------------------------------------------------------------
+class FMIndexG:
+    """FM-index over a sequence of ANY ordered elements with at most 256 distinct values: the text is
+    rank-compressed into bytes and indexed on the device once; the handle persists, so a batch of queries does not
+    rebuild the index as the reference's wrappers do (src/Data/FMIndex.hs:368,419,481,546).  A pattern is a sequence
+    of elements; one that contains an element the text does not have, or no element at all, has no occurrence
+    (countFMIndex gives Nothing: src/Data/FMIndex/Internal.hs:347-438)."""
+
+    def __init__(self, xs, sa_sample_rate: int = 1, ctx=None):
+        from .fmindex import FMIndex
+        xs = list(xs)
+        self.alphabet = Alphabet(xs)
+        self.fm = FMIndex(self.alphabet.encode(xs) if xs else None, "B", sa_sample_rate, ctx)
+
+    def _codes(self, pat):
+        pat = list(pat)
+        if not pat or any(x not in self.alphabet.rank for x in pat):
+            return None
+        return bytes(self.alphabet.rank[x] for x in pat)
+
+    def count_many(self, pats) -> list:
+        """countFMIndex per pattern: the number of occurrences, None for Nothing."""
+        coded = [self._codes(p) for p in pats]
+        live = [k for k, c in enumerate(coded) if c is not None]
+        out = [None] * len(coded)
+        if live:
+            got = self.fm.count_many([coded[k] for k in live])
+            for k, v in zip(live, got.tolist()):
+                out[k] = None if v < 0 else int(v)
+        return out
+
+    def count(self, pat):
+        return self.count_many([pat])[0]
+
+    def locate_many(self, pats) -> list:
+        """locateFMIndex per pattern: the 1-based text positions of its occurrences in suffix-array order
+        (src/Data/FMIndex.hs:473-474), [] when there is none."""
+        coded = [self._codes(p) for p in pats]
+        live = [k for k, c in enumerate(coded) if c is not None]
+        out = [[] for _ in coded]
+        if live:
+            ho, pos = self.fm.locate_many([coded[k] for k in live])
+            for i, k in enumerate(live):
+                out[k] = pos[int(ho[i]):int(ho[i + 1])].astype(np.int64).tolist()
+        return out
+
+    def locate(self, pat) -> list:
+        return self.locate_many([pat])[0]
+
+    def close(self):
+        self.fm.close()
 
 
 # ---- BWT matrix as a view, sortTB, magicInverseBWT -----------------------------------------------------------
