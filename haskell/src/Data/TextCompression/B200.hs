@@ -42,6 +42,11 @@ module Data.TextCompression.B200
   , unpackBlockW8
   , decodePackedW8
   , decodeBlocksPackedW8
+    -- * unboxed results alongside the Seq API (SURVEY.md 8f.1): packed arrays in strict ByteStrings, no per-element boxing
+  , PackedBWT (..)
+  , toBWTPackedW8
+  , fromBWTPackedW8
+  , toMTFPackedW8
     -- * Data.FMIndex.Internal replacements
   , B200FM
   , buildFMIndexW8
@@ -102,6 +107,10 @@ foreign import ccall safe "tc_bwt_decode"
   c_bwt_decode :: Ptr TcCtx -> Ptr Int16 -> Word64 -> Ptr Word8 -> Word64 -> Ptr Word64 -> IO CInt
 foreign import ccall safe "tc_mtf_encode"
   c_mtf_encode :: Ptr TcCtx -> Ptr Int16 -> Word64 -> Ptr Word16 -> Ptr Int16 -> Ptr Word32 -> IO CInt
+foreign import ccall safe "tc_bwt_decode_u8"
+  c_bwt_decode_u8 :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Word64 -> Ptr Word8 -> Word64 -> Ptr Word64 -> IO CInt
+foreign import ccall safe "tc_mtf_encode_u8"
+  c_mtf_encode_u8 :: Ptr TcCtx -> Ptr Word8 -> Word64 -> Word64 -> Ptr Word16 -> Ptr Int16 -> Ptr Word32 -> IO CInt
 foreign import ccall safe "tc_mtf_decode"
   c_mtf_decode :: Ptr TcCtx -> Ptr Word16 -> Word64 -> Ptr Int16 -> Word32 -> Ptr Int16 -> IO CInt
 foreign import ccall safe "tc_rle_encode"
@@ -397,6 +406,51 @@ decodeBlocksPackedW8 blobs = unsafePerformIO $ withB200 $ \ctx -> do
         withForeignPtr fp $ \d -> BS.packCStringLen (castPtr d, m)
       mapM_ touchForeignPtr ins
       pure res
+
+-- | The BWT of a ByteString without a `Seq (Maybe Word8)`: the n + 1 column bytes (the byte in slot `bwtPrimary` is
+-- unspecified: that slot is the Nothing) in one strict ByteString.  8f.1: results stay packed until a caller asks
+-- for the `Seq`; `toBWTW8` is `unpackBWT . toBWTPackedW8`.
+data PackedBWT = PackedBWT { bwtColumn :: !BS.ByteString, bwtPrimary :: !Int }
+
+toBWTPackedW8 :: BS.ByteString -> PackedBWT
+toBWTPackedW8 xs
+  | BS.null xs = PackedBWT BS.empty 0
+  | otherwise  = unsafePerformIO $ withB200 $ \ctx ->
+      BSU.unsafeUseAsCStringLen xs $ \(p, n) -> do
+        bwt <- pinned (n + 1)
+        alloca $ \pprim -> withForeignPtr bwt $ \pb -> do
+          c_bwt_encode ctx (castPtr p) (fromIntegral n) pb pprim nullPtr >>= check ctx
+          prim <- fromIntegral <$> peek pprim
+          col  <- BS.packCStringLen (castPtr pb, n + 1)
+          pure (PackedBWT col prim)
+
+-- | Inverse of `toBWTPackedW8` (tc_bwt_decode_u8: the column as bytes + primary, 1 byte per symbol on the device).
+fromBWTPackedW8 :: PackedBWT -> BS.ByteString
+fromBWTPackedW8 (PackedBWT col prim)
+  | BS.null col = BS.empty
+  | otherwise   = unsafePerformIO $ withB200 $ \ctx ->
+      BSU.unsafeUseAsCStringLen col $ \(p, bigN) -> do
+        out <- pinned bigN
+        alloca $ \pn -> withForeignPtr out $ \po -> do
+          c_bwt_decode_u8 ctx (castPtr p) (fromIntegral bigN) (fromIntegral prim) po (fromIntegral bigN) pn >>= check ctx
+          m <- fromIntegral <$> peek pn
+          BS.packCStringLen (castPtr po, m)
+
+-- | Move-to-front of a packed BWT (tc_mtf_encode_u8): the N indices as little-endian Word16 pairs of bytes in one
+-- strict ByteString (2 N bytes; index k is bytes 2k, 2k + 1) and the final list.
+toMTFPackedW8 :: PackedBWT -> (BS.ByteString, Seq (Maybe Word8))
+toMTFPackedW8 (PackedBWT col prim)
+  | BS.null col = (BS.empty, DS.empty)
+  | otherwise   = unsafePerformIO $ withB200 $ \ctx ->
+      BSU.unsafeUseAsCStringLen col $ \(p, bigN) -> do
+        idx <- pinned (2 * bigN)
+        fin <- pinned (2 * 257)
+        alloca $ \psig -> withForeignPtr idx $ \px -> withForeignPtr fin $ \pf -> do
+          c_mtf_encode_u8 ctx (castPtr p) (fromIntegral bigN) (fromIntegral prim) px pf psig >>= check ctx
+          sg <- fromIntegral <$> peek psig
+          fs <- peekArray sg pf
+          ix <- BS.packCStringLen (castPtr px, 2 * bigN)
+          pure (ix, DS.fromList (map i16ToMaybe fs))
 
 -- | Device-resident FM-index handle (tc_fm); freed by the GC finaliser.
 newtype B200FM = B200FM (ForeignPtr TcFm)

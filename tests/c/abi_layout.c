@@ -64,6 +64,8 @@ int main(void) {
            (tc_ctx *, uint64_t, const uint8_t *const *, const uint64_t *, int, uint8_t *const *, const uint64_t *,
             uint64_t *, tc_block_info *));
     IMPORT(tc_packed_unpack, int, (const void *, uint64_t, uint32_t *, int16_t *, uint64_t, tc_block_info *));
+    IMPORT(tc_bwt_decode_u8, int, (tc_ctx *, const uint8_t *, uint64_t, uint64_t, uint8_t *, uint64_t, uint64_t *));
+    IMPORT(tc_mtf_encode_u8, int, (tc_ctx *, const uint8_t *, uint64_t, uint64_t, uint16_t *, int16_t *, uint32_t *));
     IMPORT(tc_packed_decode, int, (tc_ctx *, const void *, uint64_t, uint8_t *, uint64_t, uint64_t *));
     IMPORT(tc_blocks_decode_packed, int, (tc_ctx *, uint64_t, const void *const *, const uint64_t *, uint8_t *const *, const uint64_t *, uint64_t *));
     IMPORT(tc_fm_build, int, (tc_ctx *, const uint8_t *, uint64_t, uint32_t, tc_fm **));
